@@ -1,0 +1,150 @@
+"""Generate tests/golden/*.npz from the INSTALLED Hugging Face implementation (transformers 5.5.0).
+
+Run in the build container only:  python oracle/gen_golden.py
+The reference repo has no tests, fixtures or golden vectors for this path; the
+arithmetic lives in `transformers` (ref:training/setup.py:22 pins >=4.35.1).  This script therefore drives
+the HF classes with a literal copy of ref:training/run_distillation.py:1453-1495 and records what they
+produce on seeded tiny inputs; tests/test_oracle.py pins oracle/*.py to these files and the -m gpu tests
+compare the CUDA path to the oracle (and to these files directly).
+
+Weights are NOT stored: both sides rebuild them from numpy's frozen RandomState via
+oracle.whisper_oracle.init_state_dict(dims, seed).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+from torch import nn
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+from oracle import whisper_oracle as wo      # noqa: E402
+from oracle import logmel_oracle as lo       # noqa: E402
+
+OUT = os.path.join(os.path.dirname(__file__), "..", "tests", "golden")
+STUDENT_SEED, TEACHER_SEED, BATCH_SEED = 11, 23, 5
+
+
+def hf_model(dims: wo.WhisperDims, sd: dict):
+    import transformers
+    from transformers import WhisperConfig, WhisperForConditionalGeneration
+    cfg = WhisperConfig(
+        vocab_size=dims.vocab_size, num_mel_bins=dims.num_mel_bins, d_model=dims.d_model,
+        encoder_layers=dims.encoder_layers, encoder_attention_heads=dims.encoder_attention_heads,
+        encoder_ffn_dim=dims.encoder_ffn_dim, decoder_layers=dims.decoder_layers,
+        decoder_attention_heads=dims.decoder_attention_heads, decoder_ffn_dim=dims.decoder_ffn_dim,
+        max_source_positions=dims.max_source_positions, max_target_positions=dims.max_target_positions,
+        pad_token_id=dims.pad_token_id, bos_token_id=dims.pad_token_id, eos_token_id=dims.pad_token_id,
+        decoder_start_token_id=dims.decoder_start_token_id, suppress_tokens=None, begin_suppress_tokens=None,
+    )
+    m = WhisperForConditionalGeneration(cfg)
+    full = dict(sd)
+    full["proj_out.weight"] = sd["model.decoder.embed_tokens.weight"]
+    missing, unexpected = m.load_state_dict(full, strict=False)
+    assert not unexpected, unexpected
+    assert all("proj_out" in k for k in missing), missing
+    assert m.proj_out.weight.data_ptr() == m.model.decoder.embed_tokens.weight.data_ptr(), "tie lost"
+    return m, transformers.__version__
+
+
+def reference_train_step(student_model, teacher_model, batch, temperature, kl_weight, share_hidden_states):
+    """Literal restatement of ref:training/run_distillation.py:1453-1495 on HF modules."""
+    from transformers.modeling_outputs import BaseModelOutput
+
+    def kl_divergence(target_distribution, log_predicted_distribution, labels):
+        kl_loss = nn.KLDivLoss(reduction="none")
+        divergence = kl_loss(log_predicted_distribution, target_distribution)
+        padding_mask = labels >= 0
+        padding_mask = padding_mask.unsqueeze(-1)
+        divergence = divergence * padding_mask
+        divergence = divergence.sum() / padding_mask.sum()
+        return divergence
+
+    student_model.train()
+    teacher_model.eval()
+    student_outputs = student_model(**batch)
+    with torch.no_grad():
+        if share_hidden_states:
+            encoder_outputs = BaseModelOutput(student_outputs.encoder_last_hidden_state)
+            teacher_outputs = teacher_model(encoder_outputs=encoder_outputs, labels=batch["labels"])
+        else:
+            teacher_outputs = teacher_model(**batch)
+    ce_loss = student_outputs.loss
+    teacher_distribution = nn.functional.softmax(teacher_outputs.logits / temperature, dim=-1)
+    student_distribution = nn.functional.log_softmax(student_outputs.logits / temperature, dim=-1)
+    kl_loss = kl_divergence(teacher_distribution, student_distribution, batch["labels"]) * temperature**2
+    loss = 0.8 * ce_loss + kl_weight * kl_loss
+    return loss, {"loss": loss, "ce_loss": ce_loss, "kl_loss": kl_loss}, student_outputs, teacher_outputs
+
+
+def gen_kd():
+    torch.set_num_threads(4)
+    sc, tc = wo.PRESETS["tiny-student"], wo.PRESETS["tiny-teacher"]
+    out = {}
+    for branch, share in (("A", False), ("B", True)):
+        ssd = wo.init_state_dict(sc, STUDENT_SEED)
+        tsd = wo.init_state_dict(tc, TEACHER_SEED)
+        if share:   # ref:training/run_distillation.py:1046-1049: teacher.model.encoder = student.model.encoder
+            for k in list(tsd):
+                if k.startswith("model.encoder."):
+                    tsd[k] = ssd[k]
+        student, ver = hf_model(sc, ssd)
+        teacher, _ = hf_model(tc, tsd)
+        if share:
+            for p in student.model.encoder.parameters():
+                p.requires_grad = False
+        batch = wo.synthetic_batch(sc, batch=3, n_tok=12, seed=BATCH_SEED)
+        loss, metrics, so, to = reference_train_step(student, teacher, batch, 2.0, 1.0, share)
+        loss.backward()
+        out[f"{branch}_loss"] = loss.detach().numpy()
+        out[f"{branch}_ce_loss"] = metrics["ce_loss"].detach().numpy()
+        out[f"{branch}_kl_loss"] = metrics["kl_loss"].detach().numpy()
+        out[f"{branch}_student_logits"] = so.logits.detach().numpy()
+        out[f"{branch}_teacher_logits"] = to.logits.detach().numpy()
+        out[f"{branch}_encoder_last_hidden_state"] = so.encoder_last_hidden_state.detach().numpy()
+        names, norms, sums = [], [], []
+        for n, p in student.named_parameters():
+            if p.grad is None:
+                continue
+            names.append(n)
+            norms.append(float(p.grad.norm()))
+            sums.append(float(p.grad.double().sum()))
+            keep = (p.grad.numel() <= 17000 and (".layers." not in n or ".layers.0." in n)) or n.endswith("embed_tokens.weight")
+            if keep:
+                out[f"{branch}_grad::{n}"] = p.grad.detach().numpy()
+        out[f"{branch}_grad_names"] = np.array(names)
+        out[f"{branch}_grad_norms"] = np.array(norms, dtype=np.float64)
+        out[f"{branch}_grad_sums"] = np.array(sums, dtype=np.float64)
+        print(branch, "loss", float(loss), "ce", float(metrics["ce_loss"]), "kl", float(metrics["kl_loss"]),
+              "n_grads", len(names))
+    out["transformers_version"] = np.array(ver)
+    out["torch_version"] = np.array(torch.__version__)
+    out["seeds"] = np.array([STUDENT_SEED, TEACHER_SEED, BATCH_SEED])
+    np.savez_compressed(os.path.join(OUT, "kd_tiny.npz"), **out)
+
+
+def gen_logmel():
+    from transformers import WhisperFeatureExtractor
+    import transformers
+    wav = lo.synthetic_waveforms(3, seed=7, ragged=False)
+    wav[1, 200000:] = 0.0                       # hard-zero tail -> clamp + floor path
+    short = wav[2, :123457].copy()              # short clip -> extractor zero-pads (HF:...:296)
+    for n_mels in (80, 128):
+        fe = WhisperFeatureExtractor(feature_size=n_mels)
+        feats = fe([wav[0], wav[1], short], sampling_rate=16000, return_tensors="np")["input_features"]
+        assert feats.shape == (3, n_mels, 3000), feats.shape
+        sel = np.r_[0:48, 1250:1298, 1476:1500 + 24, 2952:3000]
+        np.savez_compressed(
+            os.path.join(OUT, f"logmel_{n_mels}.npz"),
+            frames=sel, values=feats[:, :, sel].astype(np.float32),
+            row_mean=feats.mean(axis=2).astype(np.float64), utt_max=feats.reshape(3, -1).max(axis=1),
+            utt_min=feats.reshape(3, -1).min(axis=1),
+            mel_filters=fe.mel_filters.astype(np.float64),
+            transformers_version=np.array(transformers.__version__), seed=np.array(7), short_len=np.array(123457))
+        print("logmel", n_mels, feats.mean(), feats.min(), feats.max())
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    gen_kd()
+    gen_logmel()
