@@ -1,0 +1,30 @@
+// C-ABI plumbing: error text, version, device probe.  See include/dwb.h for the contract.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+extern "C" void dwb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* dwb_last_error(void) { return g_err; }
+extern "C" int dwb_abi_version(void) { return 1; }
+
+// 0 when a compute-capability 10.x device is current; error otherwise (the product never falls back to a CPU path)
+extern "C" int dwb_check_device(void) {
+  int dev = 0;
+  DWB_CUDA_OK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  DWB_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    dwb_set_error("distil-whisper-b200 kernels are built for sm_100a only; current device is sm_%d%d (%s)", prop.major, prop.minor,
+                  prop.name);
+    return DWB_ERR_UNSUPPORTED;
+  }
+  return DWB_OK;
+}

@@ -1,0 +1,426 @@
+// bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (fp32 accumulators in TMEM, double
+// buffered) -> epilogue warps (tcgen05.ld, bias / GELU, bf16 or fp32) -> swizzled smem panel -> TMA store /
+// TMA reduce-add.  Persistent: one CTA per SM walks a static tile list.
+//
+// Replaces every nn.Linear / Conv1d-as-GEMM the reference reaches through
+// HF:models/whisper/modeling_whisper.py:310-355 (q/k/v/out_proj), :404-407 (fc1/gelu/fc2), :619-620 (conv1/conv2),
+// :1081 (proj_out) and their autograd backward (dgrad / wgrad) under ref:training/run_distillation.py:1609.
+//
+//   C[M,N] = act(alpha * A[M,K] . B[N,K]^T + bias[N])
+// Operand storage is described per operand ("major"):
+//   K-major  (0): A is [M,K] row-major / B is [N,K] row-major      (reduction dim contiguous)  -- forward, y = x W^T
+//   MN-major (1): A is [K,M] row-major / B is [K,N] row-major      (reduction dim strided)     -- dgrad / wgrad
+// Both are fed to the tensor core directly (UMMA a_major/b_major bits); nothing is transposed in HBM.
+#include "common.cuh"
+
+namespace dwb {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kGemmThreads = 256;
+constexpr int kEpiThreads = 128;
+constexpr int kPanelBytes = 128 * 128;   // 128 rows x 128 B
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (192 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = 2 * BN;   // double-buffered accumulator (power of two: 256 or 512)
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 2 * kPanelBytes + 256;
+};
+
+struct GemmParams {
+  int M, N, K;
+  int split_k;          // >1: each work item reduces a K slice and reduce-adds fp32 into C
+  int c_f32;            // output dtype: 0 bf16, 1 fp32
+  int reduce_add;       // TMA reduce-add instead of store (fp32 only)
+  int act;              // 0 none, 1 gelu(erf)
+  float alpha;
+  const float* bias;    // [N] or null
+};
+
+template <int BN, int A_MN, int B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* panels = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(panels + 2 * kPanelBytes);
+  uint64_t* full_bar = bars;                      // [kStages]
+  uint64_t* empty_bar = bars + Cfg::kStages;      // [kStages]
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = ceil_div(p.M, BM);
+  const int n_tiles = ceil_div(p.N, BN);
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb_total = ceil_div(p.K, BK);
+  const int kb_per_split = ceil_div(num_kb_total, p.split_k);
+  const int num_items = num_tiles * p.split_k;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_c);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kEpiThreads);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int tile = item % num_tiles;
+      const int split = item / num_tiles;
+      const int m0 = (tile / n_tiles) * BM;
+      const int n0 = (tile % n_tiles) * BN;
+      const int kb0 = split * kb_per_split;
+      const int kb1 = min(kb0 + kb_per_split, num_kb_total);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(&tmap_a, &full_bar[stage], sa + j * (BK * 128), m0 + 64 * j, kb * BK);
+          } else {
+            tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BK, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(&tmap_b, &full_bar[stage], sb + j * (BK * 128), n0 + 64 * j, kb * BK);
+          } else {
+            tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * BK, n0);
+          }
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    // descriptor start-address advance (16 B units) per UMMA_K = 16 elements of K
+    constexpr uint32_t a_kstep = A_MN ? (2 * 1024) >> 4 : 32 >> 4;
+    constexpr uint32_t b_kstep = B_MN ? (2 * 1024) >> 4 : 32 >> 4;
+    constexpr uint32_t a_lbo = A_MN ? BK * 128 : 16;
+    constexpr uint32_t b_lbo = B_MN ? BK * 128 : 16;
+    int stage = 0;
+    uint32_t phase = 0;
+    int local_it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local_it) {
+      const int split = item / num_tiles;
+      const int kb0 = split * kb_per_split;
+      const int kb1 = min(kb0 + kb_per_split, num_kb_total);
+      const int acc = local_it & 1;
+      const uint32_t acc_phase = (local_it >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t da = umma_desc_sw128(sa, a_lbo, 1024);
+          const uint64_t db = umma_desc_sw128(sb, b_lbo, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            tc_mma_ss(tmem_d, da + (uint64_t)(k * a_kstep), db + (uint64_t)(k * b_kstep), idesc,
+                      (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);             // frees the smem stage once these MMAs retire
+          if (kb == kb1 - 1) tc_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+      if (kb1 <= kb0 && lane == 0) tc_commit(&tmem_full[acc]);   // empty K slice (never with sane split_k)
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue =========================================
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int row = q * 32 + lane;                // row inside the 128-row tile
+    const int epi_tid = threadIdx.x - 4 * 32;
+    const int panel_cols = p.c_f32 ? 32 : 64;
+    const int panels_per_tile = BN / panel_cols;
+    int local_it = 0;
+    int panel_it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local_it) {
+      const int tile = item % num_tiles;
+      const int m0 = (tile / n_tiles) * BM;
+      const int n0 = (tile % n_tiles) * BN;
+      const int acc = local_it & 1;
+      const uint32_t acc_phase = (local_it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      for (int pi = 0; pi < panels_per_tile; ++pi, ++panel_it) {
+        const int c0 = pi * panel_cols;
+        if (n0 + c0 >= p.N) break;                // fully out-of-range panel (N tail)
+        uint32_t v[64];
+        tmem_ld_32x32(t_row + c0, v);
+        if (!p.c_f32) tmem_ld_32x32(t_row + c0 + 32, v + 32);
+        tmem_ld_wait();
+        const bool last_panel = (pi == panels_per_tile - 1) || (n0 + c0 + panel_cols >= p.N);
+        if (last_panel) {                         // accumulator fully read: hand TMEM back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+        uint8_t* buf = panels + (panel_it & 1) * kPanelBytes;
+        if (epi_tid == 0) tma_store_wait_read<1>();
+        named_bar_sync(1, kEpiThreads);
+        uint8_t* rowp = buf + row * 128;
+        const int sw = row & 7;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {             // 8 x 16 B chunks per 128 B row
+          uint4 out;
+          if (p.c_f32) {
+            float f[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int col = n0 + c0 + j * 4 + e;
+              float x = __uint_as_float(v[j * 4 + e]) * p.alpha;
+              if (p.bias != nullptr && col < p.N) x += __ldg(p.bias + col);
+              if (p.act == 1) x = gelu_erf(x);
+              f[e] = x;
+            }
+            out = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+          } else {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int col = n0 + c0 + j * 8 + e;
+              float x = __uint_as_float(v[j * 8 + e]) * p.alpha;
+              if (p.bias != nullptr && col < p.N) x += __ldg(p.bias + col);
+              if (p.act == 1) x = gelu_erf(x);
+              f[e] = x;
+            }
+            out = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                             pack_bf16x2(f[6], f[7]));
+          }
+          *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = out;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, kEpiThreads);
+        if (epi_tid == 0) {
+          if (p.reduce_add) tma_reduce_add_2d(&tmap_c, buf, n0 + c0, m0);
+          else tma_store_2d(&tmap_c, buf, n0 + c0, m0);
+          tma_store_commit();
+        }
+      }
+    }
+    if (epi_tid == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// plain SIMT GEMM with the same contract: debugging aid and on-device cross-check for the tests.
+__global__ void gemm_bf16_simt_kernel(const bf16* __restrict__ A, int64_t lda, int a_mn, const bf16* __restrict__ B,
+                                      int64_t ldb, int b_mn, void* __restrict__ C, int64_t ldc, int c_f32, int M, int N,
+                                      int K, const float* __restrict__ bias, int act, float alpha, int accumulate) {
+  __shared__ float sa[16][17], sb[16][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    const int ka = k0 + tx;
+    sa[ty][tx] = (m < M && ka < K) ? __bfloat162float(a_mn ? A[(int64_t)ka * lda + m] : A[(int64_t)m * lda + ka]) : 0.f;
+    const int nb = blockIdx.x * 16 + ty;
+    sb[ty][tx] = (nb < N && ka < K) ? __bfloat162float(b_mn ? B[(int64_t)ka * ldb + nb] : B[(int64_t)nb * ldb + ka]) : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += sa[ty][k] * sb[tx][k];
+    __syncthreads();
+  }
+  if (m < M && n < N) {
+    float x = acc * alpha;
+    if (bias) x += bias[n];
+    if (act == 1) x = gelu_erf(x);
+    if (c_f32) {
+      float* c = reinterpret_cast<float*>(C) + (int64_t)m * ldc + n;
+      *c = accumulate ? (*c + x) : x;
+    } else {
+      reinterpret_cast<bf16*>(C)[(int64_t)m * ldc + n] = __float2bfloat16_rn(x);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+static PFN_encodeTiled g_encode = nullptr;
+PFN_encodeTiled get_encode_tiled() {
+  if (g_encode) return g_encode;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  return g_encode;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                 uint32_t box_rows, uint32_t box_cols) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) { dwb_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return DWB_ERR_CUDA; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((ld_elems * elem_bytes) & 15) != 0) {
+    dwb_set_error("TMA operand needs a 16 B aligned base and row pitch (base=%p, pitch=%llu B)", base,
+                  (unsigned long long)(ld_elems * elem_bytes));
+    return DWB_ERR_INVALID;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = enc(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    dwb_set_error("cuTensorMapEncodeTiled failed with %d (rows=%llu cols=%llu ld=%llu box=%ux%u)", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows, box_cols);
+    return DWB_ERR_CUDA;
+  }
+  return DWB_OK;
+}
+
+template <int BN, int A_MN, int B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int grid,
+                       cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DWB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, tc, p);
+  DWB_LAUNCH_OK();
+  return DWB_OK;
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_num_sms <= 0)
+      g_num_sms = kNumSMs;
+  }
+  return g_num_sms;
+}
+
+}  // namespace dwb
+
+using namespace dwb;
+
+extern "C" int dwb_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
+                             void* C, int64_t ldc, int c_f32, int M, int N, int K, const float* bias, int act,
+                             float alpha, int accumulate, int impl, void* stream) {
+  DWB_CHECK_ARG(A && B && C, "dwb_gemm_bf16: null operand");
+  DWB_CHECK_ARG(M > 0 && N > 0 && K > 0, "dwb_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
+  DWB_CHECK_ARG(!(accumulate && !c_f32), "dwb_gemm_bf16: accumulate needs an fp32 C");
+  DWB_CHECK_ARG(act == 0 || act == 1, "dwb_gemm_bf16: unknown activation %d", act);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (impl == 1) {   // SIMT cross-check implementation
+    dim3 grid(ceil_div(N, 16), ceil_div(M, 16)), block(16, 16);
+    gemm_bf16_simt_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const bf16*>(A), lda, a_mn_major,
+                                                   reinterpret_cast<const bf16*>(B), ldb, b_mn_major, C, ldc, c_f32, M,
+                                                   N, K, bias, act, alpha, accumulate);
+    DWB_LAUNCH_OK();
+    return DWB_OK;
+  }
+  DWB_CHECK_ARG(impl == 0, "dwb_gemm_bf16: unknown impl %d", impl);
+
+  // tile shape / split-K heuristic: fill 148 SMs in as few full waves as possible
+  const int sms = num_sms();
+  const int m_tiles = ceil_div(M, BM);
+  int bn = 256;
+  {
+    const int t256 = m_tiles * ceil_div(N, 256), t128 = m_tiles * ceil_div(N, 128);
+    const double w256 = (double)ceil_div(t256, sms) * 2.0, w128 = (double)ceil_div(t128, sms) * 1.0;
+    if (N <= 128 || w128 < w256) bn = 128;
+  }
+  const int tiles = m_tiles * ceil_div(N, bn);
+  const int num_kb = ceil_div(K, BK);
+  int split_k = 1;
+  if (c_f32 && bias == nullptr && act == 0 && tiles * 2 <= sms && num_kb >= 16) {
+    split_k = sms / tiles;
+    if (split_k > num_kb / 4) split_k = num_kb / 4;
+    if (split_k < 1) split_k = 1;
+    // every split must own at least one k block
+    while (split_k > 1 && ceil_div(num_kb, split_k) * (split_k - 1) >= num_kb) --split_k;
+  }
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.split_k = split_k;
+  p.c_f32 = c_f32;
+  p.reduce_add = (accumulate || split_k > 1) ? 1 : 0;
+  p.act = act;
+  p.alpha = alpha;
+  p.bias = bias;
+  if (split_k > 1 && !accumulate) {
+    DWB_CUDA_OK(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));
+  }
+
+  CUtensorMap ta, tb, tc;
+  int rc;
+  if (a_mn_major) rc = make_tmap_2d(&ta, A, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, 64);
+  else rc = make_tmap_2d(&ta, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
+  if (rc) return rc;
+  if (b_mn_major) rc = make_tmap_2d(&tb, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, 64);
+  else rc = make_tmap_2d(&tb, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)bn, BK);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tc, C, c_f32 ? 4 : 2, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, BM, c_f32 ? 32 : 64);
+  if (rc) return rc;
+
+  const int items = tiles * split_k;
+  const int grid = items < sms ? items : sms;
+  const int key = (bn == 256 ? 4 : 0) | (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
+  switch (key) {
+    case 0: return launch_gemm<128, 0, 0>(ta, tb, tc, p, grid, st);
+    case 1: return launch_gemm<128, 0, 1>(ta, tb, tc, p, grid, st);
+    case 2: return launch_gemm<128, 1, 0>(ta, tb, tc, p, grid, st);
+    case 3: return launch_gemm<128, 1, 1>(ta, tb, tc, p, grid, st);
+    case 4: return launch_gemm<256, 0, 0>(ta, tb, tc, p, grid, st);
+    case 5: return launch_gemm<256, 0, 1>(ta, tb, tc, p, grid, st);
+    case 6: return launch_gemm<256, 1, 0>(ta, tb, tc, p, grid, st);
+    default: return launch_gemm<256, 1, 1>(ta, tb, tc, p, grid, st);
+  }
+}

@@ -1,0 +1,210 @@
+"""Tensor-facing wrappers over the C ABI (include/dwb.h).  torch is used for device memory and streams only:
+every arithmetic op below runs in a kernel from libdwb.so, and every call raises if the library is absent."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _abi
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+HEAD_DIM = 64
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def _check2d(t, dtype, name):
+    if t.dim() != 2 or t.stride(1) != 1 or t.dtype != dtype or not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA {dtype} matrix with unit column stride, got "
+                         f"{tuple(t.shape)} {t.dtype} strides {t.stride()} on {t.device}")
+
+
+def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, act=0, out=None, out_dtype=BF16, alpha=1.0, accumulate=False,
+         impl=0):
+    """out[M,N] = act(alpha * A . B^T + bias).  a: [M,K] (or [K,M] when a_mn); b: [N,K] (or [K,N] when b_mn)."""
+    _check2d(a, BF16, "gemm A")
+    _check2d(b, BF16, "gemm B")
+    K, M = (a.shape if a_mn else (a.shape[1], a.shape[0]))
+    Kb, N = (b.shape if b_mn else (b.shape[1], b.shape[0]))
+    if K != Kb:
+        raise ValueError(f"gemm: reduction dims differ ({K} vs {Kb})")
+    if out is None:
+        ld = round_up(N, 8 if out_dtype == BF16 else 4)
+        buf = torch.empty((M, ld), dtype=out_dtype, device=a.device)
+        out = buf[:, :N]
+    _check2d(out, out.dtype, "gemm C")
+    if out.shape != (M, N) or out.dtype not in (BF16, F32):
+        raise ValueError(f"gemm: bad output {tuple(out.shape)} {out.dtype} for M={M} N={N}")
+    if bias is not None and (bias.dtype != F32 or bias.numel() != N or not bias.is_contiguous()):
+        raise ValueError("gemm: bias must be contiguous fp32 [N]")
+    _abi.call("dwb_gemm_bf16", _ptr(a), a.stride(0), int(a_mn), _ptr(b), b.stride(0), int(b_mn), _ptr(out), out.stride(0),
+              int(out.dtype == F32), M, N, K, _ptr(bias), int(act), float(alpha), int(accumulate), int(impl), _stream())
+    return out
+
+
+def attention_fwd(q, k, v, B, H, Sq, Sk, causal, out=None, need_lse=True, use_tc=False):
+    """q: [B*Sq, >=H*64] view, k/v: [B*Sk, .] views (unit column stride).  Returns (o [B*Sq, H*64] bf16, lse [B,H,Sq])."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _check2d(t, BF16, "attention " + n)
+    if out is None:
+        out = torch.empty((B * Sq, H * HEAD_DIM), dtype=BF16, device=q.device)
+    lse = torch.empty((B, H, Sq), dtype=F32, device=q.device) if need_lse else None
+    fn = "dwb_attention_fwd_tc" if use_tc else "dwb_attention_fwd"
+    _abi.call(fn, _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out), out.stride(0), _ptr(lse),
+              B, H, Sq, Sk, HEAD_DIM, int(causal), HEAD_DIM ** -0.5, _stream())
+    return out, lse
+
+
+def attention_bwd(q, k, v, o, dout, lse, B, H, Sq, Sk, causal, dq_out, dk_out, dv_out):
+    """Writes dq_out/dk_out/dv_out (bf16 views with the layouts of q/k/v)."""
+    dev = q.device
+    delta = torch.empty((B * H * Sq,), dtype=F32, device=dev)
+    dq_acc = torch.empty((B * Sq, H * HEAD_DIM), dtype=F32, device=dev)
+    _abi.call("dwb_attention_bwd", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(o), o.stride(0),
+              _ptr(dout), dout.stride(0), _ptr(lse), _ptr(delta), _ptr(dq_acc), _ptr(dk_out), dk_out.stride(0), _ptr(dv_out),
+              dv_out.stride(0), B, H, Sq, Sk, HEAD_DIM, int(causal), HEAD_DIM ** -0.5, _stream())
+    cast_f32_to_bf16(dq_acc, dq_out)
+    return dq_out, dk_out, dv_out
+
+
+def add_layernorm(x_in, y, gamma, beta, *, rows, d, x_rows_mod=0, write_x=True, write_ln=True, save_stats=False, eps=1e-5,
+                  x_out=None):
+    """x_new = x_in (+ y); returns (x_new fp32 or None, ln bf16 or None, mean, rstd)."""
+    dev = x_in.device
+    if write_x and x_out is None:
+        x_out = torch.empty((rows, d), dtype=F32, device=dev)
+    ln = torch.empty((rows, d), dtype=BF16, device=dev) if write_ln else None
+    mean = torch.empty((rows,), dtype=F32, device=dev) if save_stats else None
+    rstd = torch.empty((rows,), dtype=F32, device=dev) if save_stats else None
+    _abi.call("dwb_add_layernorm", _ptr(x_in), int(x_rows_mod), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(x_out if write_x else None),
+              _ptr(ln), _ptr(mean), _ptr(rstd), rows, d, float(eps), _stream())
+    return (x_out if write_x else None), ln, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dgamma, dbeta, *, rows, d, want_bf16=True):
+    dev = x.device
+    dx = torch.empty((rows, d), dtype=F32, device=dev)
+    dxb = torch.empty((rows, d), dtype=BF16, device=dev) if want_bf16 else None
+    _abi.call("dwb_layernorm_bwd", _ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres), _ptr(dx), _ptr(dxb),
+              _ptr(dgamma), _ptr(dbeta), rows, d, _stream())
+    return dx, dxb
+
+
+def cast_f32_to_bf16(src, dst=None, scale=1.0):
+    s2 = src if src.dim() == 2 else src.reshape(1, -1) if src.dim() == 1 else src.reshape(-1, src.shape[-1])
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=BF16, device=src.device)
+    d2 = dst if dst.dim() == 2 else dst.reshape(1, -1) if dst.dim() == 1 else dst.reshape(-1, dst.shape[-1])
+    _check2d(s2, F32, "cast src")
+    _check2d(d2, BF16, "cast dst")
+    _abi.call("dwb_cast_f32_to_bf16", _ptr(s2), s2.stride(0), _ptr(d2), d2.stride(0), s2.shape[0], s2.shape[1], float(scale), _stream())
+    return dst
+
+
+def cast_bf16_to_f32(src, dst=None):
+    s2 = src if src.dim() == 2 else src.reshape(-1, src.shape[-1])
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=F32, device=src.device)
+    d2 = dst if dst.dim() == 2 else dst.reshape(-1, dst.shape[-1])
+    _abi.call("dwb_cast_bf16_to_f32", _ptr(s2), s2.stride(0), _ptr(d2), d2.stride(0), s2.shape[0], s2.shape[1], _stream())
+    return dst
+
+
+def conv_weight_to_kc(w):
+    O, Cc, k = w.shape
+    assert k == 3 and w.dtype == F32 and w.is_contiguous()
+    out = torch.empty((O, 3 * Cc), dtype=BF16, device=w.device)
+    _abi.call("dwb_conv_weight_to_kc_bf16", _ptr(w), _ptr(out), O, Cc, _stream())
+    return out
+
+
+def conv_wgrad_kc_to_ck(g, O, Cc):
+    dw = torch.empty((O, Cc, 3), dtype=F32, device=g.device)
+    _abi.call("dwb_conv_wgrad_kc_to_ck", _ptr(g), _ptr(dw), O, Cc, 0, _stream())
+    return dw
+
+
+def im2col_conv1(mel):
+    B, Cc, L = mel.shape
+    assert mel.dtype == F32 and mel.is_contiguous()
+    ld = round_up(3 * Cc, 8)
+    out = torch.empty((B * L, ld), dtype=BF16, device=mel.device)
+    _abi.call("dwb_im2col_conv1", _ptr(mel), _ptr(out), B, Cc, L, ld, _stream())
+    return out
+
+
+def im2col_conv2(x, B, L, d):
+    out = torch.empty((B * (L // 2), 3 * d), dtype=BF16, device=x.device)
+    _abi.call("dwb_im2col_conv2", _ptr(x), _ptr(out), B, L, d, _stream())
+    return out
+
+
+def embed_fwd(ids, E, P, B, T, d, vocab):
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and E.dtype == P.dtype
+    x = torch.empty((B * T, d), dtype=F32, device=ids.device)
+    _abi.call("dwb_embed_fwd", _ptr(ids), _ptr(E), _ptr(P), int(E.dtype == F32), _ptr(x), B, T, d, vocab, _stream())
+    return x
+
+
+def embed_bwd(ids, dx, dE, dP, B, T, d, vocab, padding_idx):
+    _abi.call("dwb_embed_bwd", _ptr(ids), _ptr(dx), _ptr(dE), _ptr(dP), B, T, d, vocab, int(padding_idx), _stream())
+
+
+def colsum(m, out=None, accumulate=False):
+    _check2d(m, BF16, "colsum")
+    if out is None:
+        out = torch.empty((m.shape[1],), dtype=F32, device=m.device)
+    _abi.call("dwb_colsum_bf16", _ptr(m), m.stride(0), _ptr(out), m.shape[0], m.shape[1], int(accumulate), _stream())
+    return out
+
+
+def gelu_bwd(da, h):
+    assert da.is_contiguous() and h.is_contiguous()
+    dh = torch.empty_like(da)
+    _abi.call("dwb_gelu_bwd", _ptr(da), _ptr(h), _ptr(dh), da.numel(), _stream())
+    return dh
+
+
+def gelu_fwd(h):
+    y = torch.empty_like(h)
+    _abi.call("dwb_gelu_fwd", _ptr(h), _ptr(y), h.numel(), _stream())
+    return y
+
+
+def kd_loss(student_logits, teacher_logits, labels, vocab, temperature, ce_weight, kl_weight, want_grad=True):
+    """student_logits/teacher_logits: fp32 [rows, ld>=vocab] buffers.  Returns (metrics4 device tensor, dlogits bf16 or None)."""
+    rows, ld = student_logits.shape
+    dev = student_logits.device
+    ws = torch.empty((int(_abi.call("dwb_kd_loss_workspace_bytes", rows)),), dtype=torch.uint8, device=dev)
+    metrics = torch.empty((4,), dtype=F32, device=dev)
+    dl = None
+    ldd = round_up(vocab, 8)
+    if want_grad:
+        dl = torch.empty((rows, ldd), dtype=BF16, device=dev)
+    labels = labels.reshape(-1).contiguous()
+    _abi.call("dwb_kd_loss", _ptr(student_logits), _ptr(teacher_logits), student_logits.stride(0), _ptr(labels), rows, vocab,
+              float(temperature), float(ce_weight), float(kl_weight), _ptr(metrics), _ptr(dl), ldd, _ptr(ws), _stream())
+    return metrics, dl
+
+
+def grad_sumsq(g, out):
+    _abi.call("dwb_grad_sumsq", _ptr(g), g.numel(), _ptr(out), _stream())
+
+
+def adamw_step(p, g, m, v, p_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_sumsq_t, max_grad_norm, grad_scale=1.0,
+               zero_grad=True):
+    _abi.call("dwb_adamw_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p_bf16), p.numel(), float(lr), float(beta1), float(beta2),
+              float(eps), float(weight_decay), int(step), _ptr(grad_sumsq_t), float(max_grad_norm), float(grad_scale),
+              int(zero_grad), _stream())

@@ -1,0 +1,118 @@
+/* distil-whisper-b200: C ABI of the sm_100a kernel library (libdwb.so).
+ *
+ * The reference (huggingface/distil-whisper @ cc96130) has no native code and no FFI: its hot path is
+ * training/run_distillation.py:1465-1495 (train_step) calling Hugging Face Transformers' Whisper modules.  Each
+ * entry point below replaces one piece of arithmetic that path reaches; the file:line it replaces is cited per
+ * function ("ref:" = the reference repo, "HF:" = transformers 5.5.0, the version the oracle is pinned to).
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (DWB_ERR_*); dwb_last_error() gives the text (thread local).
+ *   - all pointers are DEVICE pointers unless named *_host; buffers are caller-owned, never freed or allocated here.
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream and re-entrant.
+ *   - "bf16" buffers are __nv_bfloat16; matrices are row-major with an explicit row pitch `ld*` in ELEMENTS.
+ *   - TMA-backed operands (GEMM A/B/C) need a 16-byte aligned base and a row pitch that is a multiple of 16 bytes.
+ *   - no hidden global state except immutable tables created by *_plan_create.
+ */
+#ifndef DWB_H_
+#define DWB_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DWB_OK 0
+#define DWB_ERR_INVALID (-1)
+#define DWB_ERR_CUDA (-2)
+#define DWB_ERR_UNSUPPORTED (-3)
+
+const char* dwb_last_error(void);
+int dwb_abi_version(void);
+/* 0 iff the current CUDA device is compute capability 10.x (B200).  There is no CPU fallback. */
+int dwb_check_device(void);
+
+/* ---- dense contractions (tcgen05 + TMA + TMEM) -------------------------------------------------------------
+ * C[M,N] = act(alpha * A . B^T + bias)            bf16 inputs, fp32 accumulate, C bf16 (c_f32=0) or fp32 (c_f32=1)
+ *   a_mn_major = 0: A is [M,K] (pitch lda)   1: A is stored [K,M] (pitch lda)
+ *   b_mn_major = 0: B is [N,K] (pitch ldb)   1: B is stored [K,N] (pitch ldb)
+ *   act: 0 none, 1 exact-erf GELU.  accumulate=1: C += result (fp32 C only; TMA reduce-add).
+ *   impl: 0 = tcgen05 kernel (product path), 1 = plain SIMT kernel (cross-check only).
+ * Replaces nn.Linear forward/backward at HF:models/whisper/modeling_whisper.py:310-355 (q/k/v/out_proj), :404-407
+ * and :497-500 (fc1 / gelu / fc2), :1081 (proj_out), and the two Conv1d of :619-620 after im2col. */
+int dwb_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* C, int64_t ldc,
+                  int c_f32, int M, int N, int K, const float* bias, int act, float alpha, int accumulate, int impl, void* stream);
+
+/* ---- attention (head_dim 64) ---------------------------------------------------------------------------------
+ * O = softmax(scale * Q K^T [+ causal mask]) V per (batch, head); LSE[b,h,i] = log sum_j exp(scale * q_i.k_j).
+ * Q rows are [B*Sq, ldq] with head h at columns [64h, 64h+64); likewise K, V ([B*Sk, .]) and O.
+ * Replaces F.scaled_dot_product_attention via HF:integrations/sdpa_attention.py:40-104 (called from
+ * HF:models/whisper/modeling_whisper.py:342-352 with scaling=1.0 and q pre-scaled at :310; pass scale = 64^-0.5). */
+int dwb_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                      float* lse, int B, int H, int Sq, int Sk, int head_dim, int causal, float scale, void* stream);
+/* tcgen05 / TMEM forward for the non-causal encoder self-attention (same contract, causal must be 0). */
+int dwb_attention_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                         float* lse, int B, int H, int Sq, int Sk, int head_dim, int causal, float scale, void* stream);
+/* Backward.  delta_ws: fp32 [B*H*Sq] scratch; dq_acc: fp32 [B*Sq, H*64] (zeroed here, accumulated with atomics);
+ * dk/dv: bf16 with pitches lddk/lddv.  Autograd of the same sdpa call (ref:training/run_distillation.py:1609). */
+int dwb_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o, int64_t ldo,
+                      const void* dout, int64_t lddo, const float* lse, float* delta_ws, float* dq_acc, void* dk, int64_t lddk,
+                      void* dv, int64_t lddv, int B, int H, int Sq, int Sk, int head_dim, int causal, float scale, void* stream);
+
+/* ---- residual add + LayerNorm ---------------------------------------------------------------------------------
+ * x_new[r,:] = x_in[r % x_rows_mod (0: r), :] + y[r,:] (y bf16, nullable); ln = LayerNorm(x_new; gamma, beta, eps).
+ * x_out (fp32), ln_out (bf16), mean/rstd (fp32 [rows]) are each optional.
+ * HF:models/whisper/modeling_whisper.py:392-409, :469-503 (residual + next pre-LN), :623-625 + :643, :791. */
+int dwb_add_layernorm(const float* x_in, int x_rows_mod, const void* y_bf16, const float* gamma, const float* beta, float* x_out,
+                      void* ln_out_bf16, float* mean_out, float* rstd_out, int rows, int d, float eps, void* stream);
+/* dx = dres + dLN(dy); optionally also as bf16; dgamma/dbeta are ACCUMULATED (atomicAdd). */
+int dwb_layernorm_bwd(const void* dy_bf16, const float* x, const float* mean, const float* rstd, const float* gamma,
+                      const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int rows, int d, void* stream);
+
+/* ---- casts / layout -------------------------------------------------------------------------------------------*/
+int dwb_cast_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int rows, int cols, float scale, void* stream);
+int dwb_cast_bf16_to_f32(const void* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, void* stream);
+/* Conv1d weight [O,C,3] fp32 -> bf16 [O,3C] with column k*C+c (conv2), and the inverse for its gradient. */
+int dwb_conv_weight_to_kc_bf16(const float* w, void* out_bf16, int O, int C, void* stream);
+int dwb_conv_wgrad_kc_to_ck(const float* g, float* dw, int O, int C, int accumulate, void* stream);
+/* im2col for HF:models/whisper/modeling_whisper.py:619 (conv1: mel [B,C,L] fp32 -> [B*L, ld] bf16, col c*3+k) and
+ * :620 (conv2 on channels-last x [B,L,d] bf16 -> [B*L/2, 3d], col k*d+c). */
+int dwb_im2col_conv1(const float* mel, void* out_bf16, int B, int C, int L, int ld, void* stream);
+int dwb_im2col_conv2(const void* x_bf16, void* out_bf16, int B, int L, int d, void* stream);
+
+/* ---- decoder embeddings: HF:models/whisper/modeling_whisper.py:738 (embed_tokens, padding_idx) + :755 (positions) */
+int dwb_embed_fwd(const int64_t* ids, const void* E, const void* P, int table_is_f32, float* x, int B, int T, int d, int vocab,
+                  void* stream);
+int dwb_embed_bwd(const int64_t* ids, const float* dx, float* dE, float* dP, int B, int T, int d, int vocab, int padding_idx,
+                  void* stream);
+
+/* ---- small reductions / activations ---------------------------------------------------------------------------*/
+int dwb_colsum_bf16(const void* m_bf16, int64_t ld, float* out, int rows, int cols, int accumulate, void* stream); /* bias grads */
+int dwb_gelu_bwd(const void* da, const void* h, void* dh, int64_t n, void* stream);
+int dwb_gelu_fwd(const void* h, void* y, int64_t n, void* stream);
+
+/* ---- KD loss head: ref:training/run_distillation.py:1453-1462 + :1484-1493, HF:...modeling_whisper.py:1085-1088 ----
+ * metrics4 = {loss, ce, kl, n_valid} (device).  dlogits (bf16, pitch ldd, nullable) = d loss / d student_logits.
+ * teacher_logits may be NULL (CE only).  workspace: dwb_kd_loss_workspace_bytes(rows). */
+int64_t dwb_kd_loss_workspace_bytes(int rows);
+int dwb_kd_loss(const float* student_logits, const float* teacher_logits, int64_t ld, const int64_t* labels, int rows, int vocab,
+                float temperature, float ce_weight, float kl_weight, float* metrics4, void* dlogits_bf16, int64_t ldd,
+                void* workspace, void* stream);
+
+/* ---- optimiser tail: ref:training/run_distillation.py:1610-1614 (clip_grad_norm_, AdamW.step, zero_grad) -------*/
+int dwb_grad_sumsq(const float* g, int64_t n, float* out_accum, void* stream);
+int dwb_adamw_step(float* p, float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, const float* grad_sumsq, float max_grad_norm, float grad_scale, int zero_grad,
+                   void* stream);
+
+/* ---- log-mel feature extractor: HF:models/whisper/feature_extraction_whisper.py:135-164 ------------------------
+ * plan: mel filter bank [201, n_mels] fp32 on the HOST (HF:audio_utils.py:453-544) -> device tables.
+ * wav [B, 480000] fp32 -> out [B, n_mels, 3000] fp32.  One 8-CTA cluster per utterance. */
+int dwb_logmel_plan_create(const float* mel_filters_host, int n_freq, int n_mels, void** plan_out);
+int dwb_logmel_plan_destroy(void* plan);
+int dwb_logmel(void* plan, const float* wav, int B, int n_samples, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DWB_H_ */

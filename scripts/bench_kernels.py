@@ -1,0 +1,84 @@
+"""Micro-benchmarks of individual kernels (CUDA events, L2-flushing between iterations is implicit: operands > L2).
+Usage: python scripts/bench_kernels.py [gemm] [attn]"""
+import json
+import sys
+import os
+
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+from distil_whisper_b200 import ops  # noqa: E402
+
+
+def timeit(fn, iters=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def bench_gemm():
+    out = []
+    for (M, N, K, amn, bmn, act, f32) in [
+        (48000, 1280, 1280, 0, 0, 0, 0), (48000, 3840, 1280, 0, 0, 0, 0), (48000, 5120, 1280, 0, 0, 1, 0),
+        (48000, 1280, 5120, 0, 0, 0, 0), (48000, 2560, 1280, 0, 0, 0, 0), (4096, 1280, 1280, 0, 0, 0, 0),
+        (4096, 5120, 1280, 0, 0, 1, 0), (4096, 51866, 1280, 0, 0, 0, 1), (4096, 1280, 51866, 0, 1, 0, 0),
+        (1280, 1280, 4096, 1, 1, 0, 1), (51866, 1280, 4096, 1, 1, 0, 1), (8192, 8192, 8192, 0, 0, 0, 0),
+    ]:
+        a = torch.randn((K, M) if amn else (M, K), device="cuda").bfloat16()
+        b = torch.randn((K, N) if bmn else (N, K), device="cuda").bfloat16()
+        bias = torch.zeros(N, device="cuda") if not f32 else None
+        ld = ops.round_up(N, 8)
+        c = torch.empty((M, ld), device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)[:, :N]
+        ms = timeit(lambda: ops.gemm(a, b, a_mn=bool(amn), b_mn=bool(bmn), bias=bias, act=act, out=c))
+        aT = a.t() if amn else a
+        bT = b if bmn else b.t()
+        ms_t = timeit(lambda: torch.matmul(aT, bT))
+        tf = 2.0 * M * N * K / ms / 1e9
+        out.append(dict(M=M, N=N, K=K, a_mn=amn, b_mn=bmn, act=act, f32=f32, ms=round(ms, 4), tflops=round(tf, 1),
+                        cublas_ms=round(ms_t, 4), cublas_tflops=round(2.0 * M * N * K / ms_t / 1e9, 1)))
+        print(out[-1], flush=True)
+    return out
+
+
+def bench_attn():
+    out = []
+    for (B, H, Sq, Sk, causal, tc) in [(32, 20, 1500, 1500, 0, 0), (32, 20, 1500, 1500, 0, 1), (32, 20, 128, 1500, 0, 0), (32, 20, 128, 128, 1, 0)]:
+        d = H * 64
+        qkv = torch.randn((B * Sq, 3 * d), device="cuda").bfloat16()
+        kv = torch.randn((B * Sk, 2 * d), device="cuda").bfloat16()
+        q = qkv[:, :d]
+        k, v = (qkv[:, d:2 * d], qkv[:, 2 * d:]) if Sq == Sk else (kv[:, :d], kv[:, d:])
+        o = torch.empty((B * Sq, d), device="cuda", dtype=torch.bfloat16)
+        try:
+            ms = timeit(lambda: ops.attention_fwd(q, k, v, B, H, Sq, Sk, bool(causal), out=o, use_tc=bool(tc)))
+        except Exception as ex:  # noqa: BLE001
+            print("skip", (B, H, Sq, Sk, causal, tc), ex)
+            continue
+        fl = 4.0 * B * H * Sq * Sk * 64 * (0.5 if causal else 1.0)
+        qq = q.reshape(B, Sq, H, 64).transpose(1, 2)
+        kk = k.reshape(B, Sk, H, 64).transpose(1, 2)
+        vv = v.reshape(B, Sk, H, 64).transpose(1, 2)
+        ms_t = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qq, kk, vv, is_causal=bool(causal)))
+        out.append(dict(B=B, H=H, Sq=Sq, Sk=Sk, causal=causal, tc=tc, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1),
+                        sdpa_ms=round(ms_t, 4), sdpa_tflops=round(fl / ms_t / 1e9, 1)))
+        print(out[-1], flush=True)
+    return out
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["gemm", "attn"]
+    res = {}
+    if "gemm" in which:
+        res["gemm"] = bench_gemm()
+    if "attn" in which:
+        res["attn"] = bench_attn()
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/bench_kernels.json", "w") as f:
+        json.dump(res, f, indent=1)

@@ -1,0 +1,224 @@
+"""Per-kernel parity of the non-GEMM C-ABI entry points against plain PyTorch fp32 on the GPU."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from distil_whisper_b200 import ops as o, _abi
+    _abi.call("dwb_check_device")
+    return o
+
+
+def _randn(shape, seed, scale=1.0, dtype=torch.float32):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda") * scale).to(dtype)
+
+
+def _rel(x, y):
+    return float((x.float() - y.float()).norm() / (y.float().norm() + 1e-20))
+
+
+# ---------------------------------------------------------------------------------------------- attention
+def _sdpa_ref(q, k, v, B, H, Sq, Sk, causal):
+    qf = q.float().view(B, Sq, H, 64).transpose(1, 2)
+    kf = k.float().view(B, Sk, H, 64).transpose(1, 2)
+    vf = v.float().view(B, Sk, H, 64).transpose(1, 2)
+    s = (qf @ kf.transpose(-1, -2)) * 0.125
+    if causal:
+        s = s.masked_fill(~torch.ones(Sq, Sk, dtype=torch.bool, device=q.device).tril(), float("-inf"))
+    lse = torch.logsumexp(s, dim=-1)
+    o = torch.softmax(s, dim=-1) @ vf
+    return o.transpose(1, 2).reshape(B * Sq, H * 64), lse
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk,causal", [(2, 2, 128, 128, True), (1, 3, 12, 12, True), (2, 2, 100, 1500, False),
+                                              (1, 2, 1500, 1500, False), (3, 1, 77, 50, False), (2, 20, 128, 128, True)])
+def test_attention_fwd(ops, B, H, Sq, Sk, causal):
+    d = H * 64
+    qkv = _randn((B * Sq, 3 * d), 1, 1.0, torch.bfloat16)          # fused layout: strided views
+    kv = _randn((B * Sk, 2 * d), 2, 1.0, torch.bfloat16)
+    q = qkv[:, :d]
+    k, v = (qkv[:, d:2 * d], qkv[:, 2 * d:]) if Sq == Sk else (kv[:, :d], kv[:, d:])
+    o, lse = ops.attention_fwd(q, k, v, B, H, Sq, Sk, causal)
+    o_ref, lse_ref = _sdpa_ref(q, k, v, B, H, Sq, Sk, causal)
+    assert _rel(o, o_ref) < 8e-3, _rel(o, o_ref)
+    assert torch.allclose(lse, lse_ref, atol=2e-3, rtol=1e-4)
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk,causal", [(2, 2, 128, 128, True), (1, 2, 12, 12, True), (2, 2, 100, 300, False),
+                                              (1, 1, 200, 1500, False), (2, 3, 70, 70, True)])
+def test_attention_bwd(ops, B, H, Sq, Sk, causal):
+    d = H * 64
+    q = _randn((B * Sq, d), 3, 1.0, torch.bfloat16)
+    k = _randn((B * Sk, d), 4, 1.0, torch.bfloat16)
+    v = _randn((B * Sk, d), 5, 1.0, torch.bfloat16)
+    dout = _randn((B * Sq, d), 6, 1.0, torch.bfloat16)
+    o, lse = ops.attention_fwd(q, k, v, B, H, Sq, Sk, causal)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    ops.attention_bwd(q, k, v, o, dout, lse, B, H, Sq, Sk, causal, dq, dk, dv)
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    o_ref, _ = _sdpa_ref(qf, kf, vf, B, H, Sq, Sk, causal)
+    o_ref.backward(dout.float())
+    assert _rel(dq, qf.grad) < 1.5e-2, ("dq", _rel(dq, qf.grad))
+    assert _rel(dk, kf.grad) < 1.5e-2, ("dk", _rel(dk, kf.grad))
+    assert _rel(dv, vf.grad) < 1.5e-2, ("dv", _rel(dv, vf.grad))
+
+
+# ---------------------------------------------------------------------------------------------- layernorm
+@pytest.mark.parametrize("rows,d,mod", [(37, 128, 0), (1000, 1280, 0), (300, 768, 100), (64, 1024, 0)])
+def test_add_layernorm(ops, rows, d, mod):
+    x = _randn((mod if mod else rows, d), 1, 2.0)
+    y = _randn((rows, d), 2, 1.0, torch.bfloat16)
+    g, b = _randn((d,), 3) * 0.1 + 1, _randn((d,), 4) * 0.1
+    x_new, ln, mean, rstd = ops.add_layernorm(x, y, g, b, rows=rows, d=d, x_rows_mod=mod, save_stats=True)
+    xin = x.repeat(rows // mod, 1) if mod else x
+    ref_x = xin + y.float()
+    assert torch.allclose(x_new, ref_x, atol=1e-6)
+    ref_ln = F.layer_norm(ref_x, (d,), g, b, 1e-5)
+    assert _rel(ln, ref_ln) < 4e-3
+    assert torch.allclose(mean, ref_x.mean(-1), atol=1e-5)
+    assert torch.allclose(rstd, (ref_x.var(-1, unbiased=False) + 1e-5).rsqrt(), rtol=1e-4)
+    # no-add variant
+    _, ln2, _, _ = ops.add_layernorm(xin.contiguous(), None, g, b, rows=rows, d=d, write_x=False)
+    assert _rel(ln2, F.layer_norm(xin, (d,), g, b, 1e-5)) < 4e-3
+
+
+@pytest.mark.parametrize("rows,d", [(50, 128), (4096, 1280), (333, 768)])
+def test_layernorm_bwd(ops, rows, d):
+    x = _randn((rows, d), 1, 2.0)
+    dy = _randn((rows, d), 2, 1.0, torch.bfloat16)
+    dres = _randn((rows, d), 5, 1.0)
+    g, b = _randn((d,), 3) * 0.1 + 1, _randn((d,), 4) * 0.1
+    _, _, mean, rstd = ops.add_layernorm(x, None, g, b, rows=rows, d=d, write_x=False, save_stats=True)
+    dgamma = torch.zeros(d, device="cuda")
+    dbeta = torch.zeros(d, device="cuda")
+    dx, dxb = ops.layernorm_bwd(dy, x, mean, rstd, g, dres, dgamma, dbeta, rows=rows, d=d)
+    xr, gr, br = x.clone().requires_grad_(True), g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    F.layer_norm(xr, (d,), gr, br, 1e-5).backward(dy.float())
+    assert _rel(dx, xr.grad + dres) < 1e-4, _rel(dx, xr.grad + dres)
+    assert _rel(dxb, xr.grad + dres) < 5e-3
+    assert _rel(dgamma, gr.grad) < 1e-4 and _rel(dbeta, br.grad) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------- conv stem
+@pytest.mark.parametrize("B,C,L,d", [(2, 80, 100, 128), (1, 128, 3000, 256), (3, 80, 64, 64)])
+def test_conv_stem_as_gemm(ops, B, C, L, d):
+    mel = _randn((B, C, L), 1)
+    w1, b1 = _randn((d, C, 3), 2, 0.05), _randn((d,), 3, 0.05)
+    w2, b2 = _randn((d, d, 3), 4, 0.05), _randn((d,), 5, 0.05)
+    a1 = ops.im2col_conv1(mel)
+    w1b = torch.zeros((d, a1.shape[1]), dtype=torch.bfloat16, device="cuda")
+    ops.cast_f32_to_bf16(w1.reshape(d, C * 3), w1b[:, :C * 3])
+    x1 = ops.gemm(a1, w1b, bias=b1, act=1)                                   # [B*L, d] channels-last
+    ref1 = F.gelu(F.conv1d(mel.bfloat16().float(), w1.bfloat16().float(), b1, padding=1))   # [B, d, L]
+    assert _rel(x1.view(B, L, d).transpose(1, 2), ref1) < 8e-3
+    a2 = ops.im2col_conv2(x1, B, L, d)
+    w2b = ops.conv_weight_to_kc(w2)
+    x2 = ops.gemm(a2, w2b, bias=b2, act=1)                                   # [B*L/2, d]
+    ref2 = F.gelu(F.conv1d(x1.float().view(B, L, d).transpose(1, 2), w2.bfloat16().float(), b2, stride=2, padding=1))
+    assert _rel(x2.view(B, L // 2, d).transpose(1, 2), ref2) < 8e-3
+    # weight-gradient layout round trip
+    gk = _randn((d, 3 * d), 6)
+    dw = ops.conv_wgrad_kc_to_ck(gk, d, d)
+    assert torch.equal(dw, gk.view(d, 3, d).permute(0, 2, 1).contiguous())
+
+
+# ---------------------------------------------------------------------------------------------- embeddings / small ops
+@pytest.mark.parametrize("table_dtype", [torch.float32, torch.bfloat16])
+def test_embedding_fwd_bwd(ops, table_dtype):
+    B, T, d, V, pad = 3, 12, 128, 515, 500
+    E = _randn((V, d), 1, 0.02).to(table_dtype)
+    P = _randn((32, d), 2, 0.02).to(table_dtype)
+    ids = torch.randint(0, V, (B, T), device="cuda")
+    ids[0, -3:] = pad
+    x = ops.embed_fwd(ids.contiguous(), E, P, B, T, d, V)
+    ref = E.float()[ids] + P.float()[:T]
+    assert torch.allclose(x.view(B, T, d), ref, atol=1e-6)
+    dx = _randn((B * T, d), 3)
+    dE, dP = torch.zeros((V, d), device="cuda"), torch.zeros((32, d), device="cuda")
+    ops.embed_bwd(ids.contiguous(), dx, dE, dP, B, T, d, V, pad)
+    Er = E.float().clone().requires_grad_(True)
+    Pr = P.float().clone().requires_grad_(True)
+    (F.embedding(ids, Er, padding_idx=pad) + Pr[:T]).backward(dx.view(B, T, d))
+    assert torch.allclose(dE, Er.grad, atol=1e-5) and torch.allclose(dP, Pr.grad, atol=1e-5)
+    assert float(dE[pad].abs().sum()) == 0.0
+
+
+def test_colsum_gelu_cast(ops):
+    m = _randn((1000, 520), 1, 1.0, torch.bfloat16)
+    view = m[:, :514]
+    out = ops.colsum(view)
+    assert torch.allclose(out, view.float().sum(0), atol=2e-3, rtol=1e-4)
+    ops.colsum(view, out=out, accumulate=True)
+    assert torch.allclose(out, 2 * view.float().sum(0), atol=4e-3, rtol=1e-4)
+    h = _randn((64, 256), 2, 2.0, torch.bfloat16)
+    da = _randn((64, 256), 3, 1.0, torch.bfloat16)
+    hr = h.float().requires_grad_(True)
+    F.gelu(hr).backward(da.float())
+    assert _rel(ops.gelu_bwd(da, h), hr.grad) < 6e-3
+    assert _rel(ops.gelu_fwd(h), F.gelu(h.float())) < 6e-3
+    src = _randn((33, 64), 4)
+    dst = torch.zeros((33, 200), dtype=torch.bfloat16, device="cuda")
+    ops.cast_f32_to_bf16(src, dst[:, 64:128], scale=0.5)
+    assert torch.equal(dst[:, 64:128], (src * 0.5).bfloat16()) and float(dst[:, :64].abs().sum()) == 0
+    back = ops.cast_bf16_to_f32(dst[:, 64:128])
+    assert torch.equal(back, dst[:, 64:128].float())
+
+
+# ---------------------------------------------------------------------------------------------- KD loss
+@pytest.mark.parametrize("rows,V,T", [(36, 515, 2.0), (64, 51866, 2.0), (20, 1000, 1.0), (16, 515, 3.5)])
+def test_kd_loss_against_reference_formula(ops, rows, V, T):
+    from oracle import whisper_oracle as wo
+    ld = ops.round_up(V, 8)
+    s_buf = _randn((rows, ld), 1, 3.0)
+    t_buf = _randn((rows, ld), 2, 3.0)
+    s_buf[:, V:] = float("nan")            # padding columns must never be read into the result
+    t_buf[:, V:] = float("nan")
+    labels = torch.randint(0, V, (rows,), device="cuda")
+    labels[::5] = -100
+    metrics, dl = ops.kd_loss(s_buf, t_buf, labels, V, T, 0.8, 1.0)
+    s = s_buf[:, :V].clone().requires_grad_(True)
+    t = t_buf[:, :V]
+    ce = F.cross_entropy(s, labels)
+    kl = wo.kl_divergence(F.softmax(t / T, -1), F.log_softmax(s / T, -1), labels) * T ** 2      # ref :1453-1462,:1486-1490
+    loss = 0.8 * ce + 1.0 * kl
+    loss.backward()
+    m = metrics.cpu()
+    assert math.isclose(m[1], ce.item(), rel_tol=2e-5) and math.isclose(m[2], kl.item(), rel_tol=2e-4, abs_tol=1e-7)
+    assert math.isclose(m[0], loss.item(), rel_tol=2e-5) and int(m[3]) == int((labels >= 0).sum())
+    assert _rel(dl[:, :V], s.grad) < 5e-3, _rel(dl[:, :V], s.grad)
+    assert float(dl[:, V:].float().abs().sum()) == 0.0
+    assert float(dl[::5].float().abs().sum()) == 0.0
+    # CE-only (no teacher) == HF CrossEntropyLoss path
+    m2, _ = ops.kd_loss(s_buf, None, labels, V, 1.0, 1.0, 0.0, want_grad=False)
+    assert math.isclose(m2.cpu()[0], ce.item(), rel_tol=2e-5)
+
+
+# ---------------------------------------------------------------------------------------------- optimiser
+@pytest.mark.parametrize("wd,max_norm", [(0.0, 1.0), (0.01, 0.05), (0.0, 0.0)])
+def test_adamw_matches_torch(ops, wd, max_norm):
+    n = 100003
+    p0, grads = _randn((n,), 1), [_randn((n,), 10 + i, 0.3) for i in range(3)]
+    p_ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([p_ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+    p, m, v = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    pb = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    for step, g in enumerate(grads, 1):
+        p_ref.grad = g.clone()
+        if max_norm > 0:
+            torch.nn.utils.clip_grad_norm_([p_ref], max_norm)
+        opt.step()
+        gg = g.clone()
+        ss = torch.zeros(1, device="cuda")
+        ops.grad_sumsq(gg, ss)
+        assert math.isclose(float(ss), float((g.double() ** 2).sum()), rel_tol=1e-4)
+        ops.adamw_step(p, gg, m, v, pb, 1e-3, 0.9, 0.999, 1e-8, wd, step, ss if max_norm > 0 else None, max_norm)
+        assert float(gg.abs().sum()) == 0.0
+    assert torch.allclose(p, p_ref.detach(), atol=2e-6, rtol=1e-5)
+    assert torch.equal(pb, p.bfloat16())
