@@ -1,0 +1,251 @@
+#!/usr/bin/env python
+"""KD-step throughput of the B200-native path (BASELINE.json metric: KD-step utterances/s, distil-large-v3 student <-
+large-v3 teacher, batch 32 x (80 x 3000 mel, 128 tokens) per GPU, bf16).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    # the reference's own CPU implementation (HF modules)
+
+One JSON line on rank 0.  `value` = utterances/s with the batch already in HBM; `e2e` = the same step with the batch in
+pinned HOST memory (H2D copy and the D2H read of the loss inside the timed region).  `roofline` is measured live with
+CUDA events around every tcgen05 GEMM launch of the timed region.  Timing: barrier + synchronize on both sides, CUDA
+events, max over ranks.  L2: the step's working set (4.6 GB of weights + activations) is far larger than L2, no flush.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+STUDENT = dict(vocab_size=51866, num_mel_bins=80, d_model=1280, encoder_layers=32, encoder_attention_heads=20, encoder_ffn_dim=5120,
+               decoder_layers=2, decoder_attention_heads=20, decoder_ffn_dim=5120, max_source_positions=1500,
+               max_target_positions=448, pad_token_id=50256, decoder_start_token_id=50258)
+TEACHER = dict(STUDENT, decoder_layers=32)
+BATCH, N_TOK = 32, 128
+# algorithmic FLOPs per utterance of the frozen-encoder recipe (variant B of BASELINE.md section 2): encoder fwd once,
+# teacher decoder + LM head fwd, student decoder + LM head fwd + bwd (2x)
+TF_PER_UTT_B = (2272.7 + 553.6 + 3 * 50.5) / 1e3
+
+
+def synthetic_batch(batch, n_tok, seed, dims, device="cpu"):
+    """mel-like features in [-1, 1.5]; ragged label rows (length ~U[n_tok/2, n_tok]) whose tail is
+    pad / -100; decoder_input_ids = labels shifted right with SOT (ref:training/run_distillation.py:460-476)."""
+    g = torch.Generator().manual_seed(seed)
+    feats = (0.5 * torch.randn((batch, dims["num_mel_bins"], 2 * dims["max_source_positions"]), generator=g)).clamp_(-1.0, 1.5)
+    hi = min(dims["pad_token_id"], dims["decoder_start_token_id"]) - 1
+    ids = torch.randint(0, hi, (batch, n_tok + 1), generator=g)
+    ids[:, 0] = dims["decoder_start_token_id"]
+    lens = torch.randint(n_tok // 2, n_tok + 2, (batch,), generator=g)
+    lens[-1] = n_tok + 1
+    pos = torch.arange(n_tok + 1)[None, :]
+    valid = pos < lens[:, None]
+    ids = torch.where(valid, ids, torch.full_like(ids, dims["pad_token_id"]))
+    dec_in = ids[:, :-1].contiguous()
+    labels = torch.where(valid[:, 1:], ids[:, 1:], torch.full_like(ids[:, 1:], -100)).contiguous()
+    return {"input_features": feats.to(device), "decoder_input_ids": dec_in.to(device), "labels": labels.to(device)}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (the recipe's clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        mx = max((float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()), default=None)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:  # noqa: BLE001
+        return 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
+
+
+def run_reference(args):
+    """The reference's own CPU path (HF modules + train_step restatement) on a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.reference_step import ReferenceKDStep
+    from oracle.whisper_oracle import WhisperDims
+    b = args.cpu_batch
+    ref = ReferenceKDStep(WhisperDims(**STUDENT), WhisperDims(**TEACHER), freeze_encoder=True)
+    batch = synthetic_batch(b, N_TOK, 1234, STUDENT)
+    sec, loss = ref.time_steps(batch, args.steps, args.warmup)
+    val = b / sec
+    cb = {"value": val, "unit": "utterances/s", "cores": ref.cores, "kind": ref.kind,
+          "sample": f"{b} utterances per step (same models, 80x3000 mel, {N_TOK} tokens, fp32 on host cores)"}
+    print(json.dumps({
+        "impl": "reference", "metric": "kd_step_utterances_per_s", "value": val, "unit": "utterances/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "distil-large-v3 student + large-v3 teacher KD step, frozen+shared encoder (README recipe), "
+                               f"{b}x(80x3000 mel, {N_TOK} tok) per step on CPU", "global_batch": b, "seq_len": N_TOK, "parallelism": "cpu"},
+        "cpu_baseline": cb, "e2e": {"value": val, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "loss": loss}))
+
+
+def build_models(device):
+    from distil_whisper_b200.modeling import DistilWhisperB200ForConditionalGeneration
+    torch.manual_seed(0)
+    with torch.device(device):
+        student = DistilWhisperB200ForConditionalGeneration(STUDENT)
+        teacher = DistilWhisperB200ForConditionalGeneration(TEACHER)
+    teacher = teacher.to(torch.bfloat16)                                   # ref :985-992 teacher_dtype bf16
+    for p in student.model.encoder.parameters():                          # ref :1023-1026 --freeze_encoder
+        p.requires_grad = False
+    return student, teacher
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-batch", type=int, default=2, help="utterances per CPU reference step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    from distil_whisper_b200 import _abi, ddp, ops
+    from distil_whisper_b200.kd import DistillationStep
+    from distil_whisper_b200.optim import FusedAdamW
+    rank, local, world = ddp.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _abi.call("dwb_check_device")
+    student, teacher = build_models(dev)
+    ddp.broadcast_parameters(student)
+    ddp.broadcast_parameters(teacher)
+    step = DistillationStep(student, teacher, kl_weight=1.0)
+    opt = FusedAdamW.for_model(student, lr=1e-4, weight_decay=0.0, max_grad_norm=1.0)
+    host_batch = {k: v.pin_memory() for k, v in synthetic_batch(BATCH, N_TOK, 1234 + rank, STUDENT).items()}
+    dev_batch = {k: v.to(dev) for k, v in host_batch.items()}
+
+    def one_step(batch):
+        loss, metrics = step.train_step(batch, temperature=2.0)
+        loss.backward()
+        opt.all_reduce_gradients()          # THE multi-GPU collective: one NCCL all-reduce of the flat student gradients
+        opt.step()
+        opt.zero_grad()
+        return loss
+
+    def timed(fn, n):
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            fn()
+        e.record()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        return ddp.max_over_ranks(s.elapsed_time(e) / 1e3 / n)      # seconds per step, max over ranks
+
+    # ---- device-resident measurement (value) + live GEMM roofline ----
+    for _ in range(args.warmup):
+        one_step(dev_batch)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _abi.LAUNCHES[0] = 0
+    ops.GEMM_PROFILE = []
+    sec = timed(lambda: one_step(dev_batch), args.steps)
+    launches = _abi.LAUNCHES[0]
+    prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+    clocks = sampler.stop() if rank == 0 else None
+    gemm_ms = sum(s.elapsed_time(e) for s, e, _ in prof)
+    gemm_flops = sum(f for _, _, f in prof)
+    # ---- end to end through the public API with host buffers ----
+    def e2e_step():
+        b = {k: v.to(dev, non_blocking=True) for k, v in host_batch.items()}
+        loss = one_step(b)
+        return float(loss.item())           # D2H read of the step's result
+    e2e_step()
+    sec_e2e = timed(e2e_step, args.steps)
+    final_loss = float(one_step(dev_batch).item())
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    utt = BATCH * world
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "gemm_dram_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    out = {
+        "metric": "kd_step_utterances_per_s", "value": utt / sec, "unit": "utterances/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "configs[1]: distil-large-v3 student + large-v3 teacher KD step (fwd student+teacher, fused CE+KL, "
+                               "bwd, grad all-reduce, clip, AdamW), frozen+shared encoder = README/paper recipe (BASELINE.md variant B), "
+                               f"{BATCH}x(80x3000 mel, {N_TOK} tok) per GPU", "global_batch": utt, "seq_len": N_TOK,
+                   "parallelism": f"dp{world}", "l2": "working set >> 126 MB L2, no flush", "variant": "B (--freeze_encoder)",
+                   "algorithmic_tflop_per_utt": TF_PER_UTT_B},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "gemm_bf16_tcgen05_kernel (all launches of the timed region)",
+                     "peak_source": peak_src, "gemm_share_of_step": gemm_ms * 1e-3 / args.steps / sec if sec > 0 else None,
+                     "gemm_launches": len(prof)},
+        "step_roofline": {"achieved_tflops_per_gpu": utt / sec * TF_PER_UTT_B / world, "frac_of_peak": utt / sec * TF_PER_UTT_B / world / peak},
+        "e2e": {"value": utt / sec_e2e, "unit": "utterances/s",
+                "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host_batch.values()), "d2h_bytes_per_step": 4},
+        "gpu_launches": launches, "clocks": clocks, "loss": final_loss,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            from oracle.reference_step import ReferenceKDStep
+            from oracle.whisper_oracle import WhisperDims
+            ref = ReferenceKDStep(WhisperDims(**STUDENT), WhisperDims(**TEACHER), freeze_encoder=True)
+            b = args.cpu_batch
+            s_cpu, _ = ref.time_steps(synthetic_batch(b, N_TOK, 1234, STUDENT), 2, 1)
+            out["cpu_baseline"] = {"value": b / s_cpu, "unit": "utterances/s", "cores": ref.cores, "kind": ref.kind,
+                                   "sample": f"2 timed steps of {b} utterances (same models and shapes, fp32, HF modules on host cores)"}
+        except Exception as ex:  # noqa: BLE001
+            out["cpu_baseline"] = {"value": None, "unit": "utterances/s", "cores": os.cpu_count(), "kind": "reference",
+                                   "sample": f"failed: {type(ex).__name__}: {ex}"}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -65,6 +65,11 @@ def header_symbols(path: str = HEADER_PATH):
 
 _lib = None
 
+# kernel launches issued through the ABI (bench.py reads / resets LAUNCHES[0]); entry -> kernels it launches
+LAUNCHES = [0]
+_KERNELS_PER_CALL = {"dwb_attention_bwd": 2, "dwb_kd_loss": 3, "dwb_last_error": 0, "dwb_abi_version": 0, "dwb_check_device": 0,
+                     "dwb_kd_loss_workspace_bytes": 0, "dwb_logmel_plan_create": 0, "dwb_logmel_plan_destroy": 0}
+
 
 def load() -> C.CDLL:
     """Load libdwb.so (built by __graft_entry__.build() / make -C distil_whisper_b200/csrc)."""
@@ -88,6 +93,7 @@ def call(name: str, *args):
     """Invoke an entry point; non-zero status -> DwbError carrying dwb_last_error()."""
     lib = load()
     rc = getattr(lib, name)(*args)
+    LAUNCHES[0] += _KERNELS_PER_CALL.get(name, 1)
     if name in _NO_STATUS:
         return rc
     if rc != 0:

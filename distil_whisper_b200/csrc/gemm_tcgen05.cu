@@ -28,7 +28,7 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (192 * 1024) / kStageBytes;
   static constexpr int kTmemCols = 2 * BN;   // double-buffered accumulator (power of two: 256 or 512)
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 2 * kPanelBytes + 256;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 2 * kPanelBytes + 256 + BN * 4;
 };
 
 struct GemmParams {
@@ -55,6 +55,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint64_t* tmem_full = bars + 2 * Cfg::kStages;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;           // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(bars) + 64;   // [BN] fp32, 256 B past the barriers
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -173,6 +174,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int epi_tid = threadIdx.x - 4 * 32;
     const int panel_cols = p.c_f32 ? 32 : 64;
     const int panels_per_tile = BN / panel_cols;
+    const uint32_t row_saddr = smem_u32(panels) + row * 128;
+    const int sw = row & 7;
     int local_it = 0;
     int panel_it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local_it) {
@@ -181,6 +184,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int n0 = (tile % n_tiles) * BN;
       const int acc = local_it & 1;
       const uint32_t acc_phase = (local_it >> 1) & 1;
+      // stage this tile's bias slice once (zeros when there is no bias): read back as warp-uniform LDS broadcasts.
+      // Safe to overwrite: every thread is past the previous tile's last named barrier, i.e. past its last read.
+      float* sb = s_bias;
+      for (int c = epi_tid; c < BN; c += kEpiThreads) sb[c] = (p.bias != nullptr && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -196,45 +203,42 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           tc_fence_before();
           mbar_arrive(&tmem_empty[acc]);
         }
-        uint8_t* buf = panels + (panel_it & 1) * kPanelBytes;
+        const uint32_t buf_off = (panel_it & 1) * kPanelBytes;
         if (epi_tid == 0) tma_store_wait_read<1>();
-        named_bar_sync(1, kEpiThreads);
-        uint8_t* rowp = buf + row * 128;
-        const int sw = row & 7;
+        named_bar_sync(1, kEpiThreads);           // panel buffer free again + bias slice visible
+        const float4* sb4 = reinterpret_cast<const float4*>(sb + c0);
+        if (p.c_f32) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {             // 8 x 16 B chunks per 128 B row
-          uint4 out;
-          if (p.c_f32) {
-            float f[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int col = n0 + c0 + j * 4 + e;
-              float x = __uint_as_float(v[j * 4 + e]) * p.alpha;
-              if (p.bias != nullptr && col < p.N) x += __ldg(p.bias + col);
-              if (p.act == 1) x = gelu_erf(x);
-              f[e] = x;
-            }
-            out = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
-          } else {
-            float f[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int col = n0 + c0 + j * 8 + e;
-              float x = __uint_as_float(v[j * 8 + e]) * p.alpha;
-              if (p.bias != nullptr && col < p.N) x += __ldg(p.bias + col);
-              if (p.act == 1) x = gelu_erf(x);
-              f[e] = x;
-            }
-            out = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                             pack_bf16x2(f[6], f[7]));
+          for (int j = 0; j < 8; ++j) {           // 8 x 16 B chunks (4 fp32) per 128 B row
+            const float4 bb = sb4[j];
+            float f0 = fmaf(__uint_as_float(v[j * 4 + 0]), p.alpha, bb.x), f1 = fmaf(__uint_as_float(v[j * 4 + 1]), p.alpha, bb.y);
+            float f2 = fmaf(__uint_as_float(v[j * 4 + 2]), p.alpha, bb.z), f3 = fmaf(__uint_as_float(v[j * 4 + 3]), p.alpha, bb.w);
+            if (p.act == 1) { f0 = gelu_erf(f0); f1 = gelu_erf(f1); f2 = gelu_erf(f2); f3 = gelu_erf(f3); }
+            st_shared_v4(row_saddr + buf_off + ((j ^ sw) << 4), __float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2),
+                         __float_as_uint(f3));
           }
-          *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = out;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {           // 8 x 16 B chunks (8 bf16) per 128 B row
+            const float4 b0 = sb4[2 * j], b1 = sb4[2 * j + 1];
+            float f[8];
+            f[0] = fmaf(__uint_as_float(v[j * 8 + 0]), p.alpha, b0.x); f[1] = fmaf(__uint_as_float(v[j * 8 + 1]), p.alpha, b0.y);
+            f[2] = fmaf(__uint_as_float(v[j * 8 + 2]), p.alpha, b0.z); f[3] = fmaf(__uint_as_float(v[j * 8 + 3]), p.alpha, b0.w);
+            f[4] = fmaf(__uint_as_float(v[j * 8 + 4]), p.alpha, b1.x); f[5] = fmaf(__uint_as_float(v[j * 8 + 5]), p.alpha, b1.y);
+            f[6] = fmaf(__uint_as_float(v[j * 8 + 6]), p.alpha, b1.z); f[7] = fmaf(__uint_as_float(v[j * 8 + 7]), p.alpha, b1.w);
+            if (p.act == 1) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+            }
+            st_shared_v4(row_saddr + buf_off + ((j ^ sw) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                         pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          }
         }
         fence_proxy_async_smem();
         named_bar_sync(2, kEpiThreads);
         if (epi_tid == 0) {
-          if (p.reduce_add) tma_reduce_add_2d(&tmap_c, buf, n0 + c0, m0);
-          else tma_store_2d(&tmap_c, buf, n0 + c0, m0);
+          if (p.reduce_add) tma_reduce_add_2d(&tmap_c, panels + buf_off, n0 + c0, m0);
+          else tma_store_2d(&tmap_c, panels + buf_off, n0 + c0, m0);
           tma_store_commit();
         }
       }

@@ -1,0 +1,101 @@
+"""The knowledge-distillation step with the reference's call surface.
+
+`DistillationStep(student, teacher, kl_weight, share_hidden_states).train_step(batch, temperature)` returns
+`(loss, {"loss", "ce_loss", "kl_loss"})` exactly like the closure at ref:training/run_distillation.py:1465-1495, and
+`eval_step(batch)` mirrors :1498-1522 (temperature 1).  `loss.backward()` (ref :1609) runs the CUDA backward.
+
+Fused relative to the reference: the two [B, T, V] logits tensors are reduced by ONE kernel (dwb_kd_loss) that
+produces CE, KL and d loss / d student_logits (bf16) together -- softmax(t/T), log_softmax(s/T), KLDivLoss, the mask
+and the mean (ref :1453-1462, :1484-1493) never exist as tensors.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import engine, ops
+
+
+class _KDStepFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, step, batch, temperature, loss_scale, anchor):
+        student, teacher = step.student, step.teacher
+        cfg = student.config
+        feats, dec_in, labels = batch["input_features"], batch["decoder_input_ids"], batch["labels"]
+        B, T = dec_in.shape
+        V = cfg.vocab_size
+        if teacher.config.vocab_size != V:
+            raise ValueError("student and teacher vocabularies differ")
+        train = ctx is not None
+        # ---- student (ref :1472)
+        enc_s, S = engine.run_encoder(student, feats, None)
+        sst = engine.state_of(student.model.decoder)
+        hf_s, dctx = engine.decoder_forward(sst, dec_in, enc_s, B, S, save=train)
+        logits_s = engine.lm_head(sst, hf_s)
+        # ---- teacher, no grad (ref :1473-1481)
+        tst = engine.state_of(teacher.model.decoder)
+        if step.share_hidden_states:
+            # teacher(encoder_outputs=student states, labels=labels): its decoder inputs are rebuilt from the labels
+            # (HF:models/whisper/modeling_whisper.py:1064-1067), which differs from the student's on prompt-masked rows
+            t_in = engine.shift_tokens_right(labels, teacher.config.pad_token_id, teacher.config.decoder_start_token_id)
+            enc_t = enc_s
+        else:
+            t_in = dec_in
+            enc_t, _ = engine.run_encoder(teacher, feats, None)
+        hf_t, _ = engine.decoder_forward(tst, t_in, enc_t, B, S, save=False)
+        logits_t = engine.lm_head(tst, hf_t)
+        # ---- fused loss head (ref :1484-1493)
+        metrics, dl = ops.kd_loss(logits_s, logits_t, labels, V, temperature, 0.8 * loss_scale, step.kl_weight * loss_scale,
+                                  want_grad=train)
+        if train:
+            ctx.step, ctx.dctx, ctx.dl = step, dctx, dl
+        step.last_student_logits = logits_s.view(B, T, -1)[:, :, :V] if step.keep_logits else None
+        step.last_teacher_logits = logits_t.view(B, T, -1)[:, :, :V] if step.keep_logits else None
+        step.last_encoder_states = enc_s
+        return metrics[0].clone(), metrics
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_metrics):
+        # d loss / d logits was produced by the loss kernel with loss_scale folded in; `loss.backward()` supplies 1.
+        step = ctx.step
+        engine.decoder_backward(engine.state_of(step.student.model.decoder), ctx.dctx, ctx.dl)
+        ctx.dctx = ctx.dl = None
+        return None, None, None, None, None
+
+
+class DistillationStep:
+    """Holds the student / teacher pair the way the reference's closures capture them (ref :1449, :1046-1049)."""
+
+    def __init__(self, student, teacher, kl_weight: float = 1.0, share_hidden_states: bool | None = None, keep_logits=False):
+        self.student, self.teacher = student, teacher
+        self.kl_weight = float(kl_weight)
+        if share_hidden_states is None:      # ref :1046: training_args.freeze_encoder and same d_model
+            enc_frozen = not any(p.requires_grad for n, p in student.model.encoder.named_parameters())
+            share_hidden_states = enc_frozen and student.config.d_model == teacher.config.d_model
+        self.share_hidden_states = bool(share_hidden_states)
+        if self.share_hidden_states:         # ref :1047-1049
+            teacher.model.encoder = student.model.encoder
+        self.keep_logits = keep_logits
+        self.last_student_logits = self.last_teacher_logits = self.last_encoder_states = None
+
+    def _anchor(self):
+        return next((p for p in self.student.model.decoder.parameters() if p.requires_grad), None)
+
+    def train_step(self, batch, temperature: float = 2.0, loss_scale: float = 1.0):
+        """loss_scale: fold 1/gradient_accumulation_steps here (the gradient is produced inside the loss kernel)."""
+        self.student.train()
+        self.teacher.eval()
+        anchor = self._anchor()
+        if anchor is None:
+            raise RuntimeError("student has no trainable decoder parameters")
+        engine._check_trainable_dtypes(self.student)
+        if any(p.requires_grad for n, p in self.student.model.encoder.named_parameters() if "embed_positions" not in n):
+            raise NotImplementedError("trainable student encoder (variant A) is not built yet; use the --freeze_encoder recipe")
+        loss, m = _KDStepFn.apply(self, batch, float(temperature), float(loss_scale), anchor)
+        return loss, {"loss": loss, "ce_loss": m[1], "kl_loss": m[2]}
+
+    @torch.no_grad()
+    def eval_step(self, batch):
+        self.student.eval()
+        self.teacher.eval()
+        _, m = _KDStepFn.forward(None, self, batch, 1.0, 1.0, None)
+        return {"loss": m[0], "ce_loss": m[1], "kl_loss": m[2]}

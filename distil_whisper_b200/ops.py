@@ -11,6 +11,8 @@ from . import _abi
 BF16 = torch.bfloat16
 F32 = torch.float32
 HEAD_DIM = 64
+# bench.py sets this to a list to time every tcgen05 GEMM launch with CUDA events: (start, end, 2*M*N*K) per launch
+GEMM_PROFILE = None
 
 
 def _ptr(t):
@@ -49,8 +51,15 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, act=0, out=None, out_dtype=
         raise ValueError(f"gemm: bad output {tuple(out.shape)} {out.dtype} for M={M} N={N}")
     if bias is not None and (bias.dtype != F32 or bias.numel() != N or not bias.is_contiguous()):
         raise ValueError("gemm: bias must be contiguous fp32 [N]")
+    prof = GEMM_PROFILE
+    if prof is not None and impl == 0:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     _abi.call("dwb_gemm_bf16", _ptr(a), a.stride(0), int(a_mn), _ptr(b), b.stride(0), int(b_mn), _ptr(out), out.stride(0),
               int(out.dtype == F32), M, N, K, _ptr(bias), int(act), float(alpha), int(accumulate), int(impl), _stream())
+    if prof is not None and impl == 0:
+        ev1.record()
+        prof.append((ev0, ev1, 2.0 * M * N * K))
     return out
 
 

@@ -31,8 +31,10 @@ def bench_gemm():
         (4096, 5120, 1280, 0, 0, 1, 0), (4096, 51866, 1280, 0, 0, 0, 1), (4096, 1280, 51866, 0, 1, 0, 0),
         (1280, 1280, 4096, 1, 1, 0, 1), (51866, 1280, 4096, 1, 1, 0, 1), (8192, 8192, 8192, 0, 0, 0, 0),
     ]:
-        a = torch.randn((K, M) if amn else (M, K), device="cuda").bfloat16()
-        b = torch.randn((K, N) if bmn else (N, K), device="cuda").bfloat16()
+        def mk(r, c):
+            return torch.randn((r, ops.round_up(c, 8)), device="cuda").bfloat16()[:, :c]
+        a = mk(K, M) if amn else mk(M, K)
+        b = mk(K, N) if bmn else mk(N, K)
         bias = torch.zeros(N, device="cuda") if not f32 else None
         ld = ops.round_up(N, 8)
         c = torch.empty((M, ld), device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)[:, :N]

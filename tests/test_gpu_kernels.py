@@ -51,6 +51,25 @@ def test_attention_fwd(ops, B, H, Sq, Sk, causal):
     assert torch.allclose(lse, lse_ref, atol=2e-3, rtol=1e-4)
 
 
+@pytest.mark.parametrize("B,H,Sq,Sk", [(2, 2, 1500, 1500), (1, 3, 300, 300), (2, 2, 128, 128), (1, 1, 100, 700), (3, 20, 50, 50)])
+def test_attention_fwd_tcgen05(ops, B, H, Sq, Sk):
+    """tcgen05 / TMEM encoder attention vs torch fp32 and vs the mma.sync kernel (same C-ABI contract)."""
+    d = H * 64
+    qkv = _randn((B * Sq, 3 * d), 11, 1.0, torch.bfloat16)
+    kv = _randn((B * Sk, 2 * d), 12, 1.0, torch.bfloat16)
+    q = qkv[:, :d]
+    k, v = (qkv[:, d:2 * d], qkv[:, 2 * d:]) if Sq == Sk else (kv[:, :d], kv[:, d:])
+    o, lse = ops.attention_fwd(q, k, v, B, H, Sq, Sk, False, use_tc=True)
+    o_ref, lse_ref = _sdpa_ref(q, k, v, B, H, Sq, Sk, False)
+    assert _rel(o, o_ref) < 8e-3, _rel(o, o_ref)
+    assert torch.allclose(lse, lse_ref, atol=2e-3, rtol=1e-4)
+    o2, _ = ops.attention_fwd(q, k, v, B, H, Sq, Sk, False, use_tc=False)
+    assert _rel(o, o2.float()) < 8e-3
+    from distil_whisper_b200._abi import DwbError
+    with pytest.raises(DwbError):
+        ops.attention_fwd(q, k, v, B, H, Sq, Sk, True, use_tc=True)      # causal is the other kernel's job
+
+
 @pytest.mark.parametrize("B,H,Sq,Sk,causal", [(2, 2, 128, 128, True), (1, 2, 12, 12, True), (2, 2, 100, 300, False),
                                               (1, 1, 200, 1500, False), (2, 3, 70, 70, True)])
 def test_attention_bwd(ops, B, H, Sq, Sk, causal):

@@ -1,0 +1,179 @@
+"""End-to-end parity of the CUDA KD step (through the reference-shaped Python surface, every kernel behind the C ABI)
+against the oracle and the committed HF 5.5.0 golden vectors.
+
+Tolerances: the kernels compute in bf16 with fp32 accumulation (BASELINE.json config 2 is bf16); bf16 has an 8-bit
+mantissa (eps 7.8e-3), so element-wise agreement with the fp32 oracle is bounded by ~1e-2 relative L2, not by the
+1e-3 the north star quotes for fp16.  Scalars that average over many elements (loss, ce, kl) are held to 2e-3."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import whisper_oracle as wo
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+
+LOGITS_REL = 1.5e-2
+GRAD_REL = 4e-2
+LOSS_REL = 2e-3
+
+
+def _rel(x, y):
+    x, y = torch.as_tensor(x).double().cpu(), torch.as_tensor(y).double().cpu()
+    return float((x - y).norm() / (y.norm() + 1e-30))
+
+
+def _build(dims, sd, dtype=torch.float32, freeze_encoder=False):
+    from distil_whisper_b200.modeling import DistilWhisperB200ForConditionalGeneration
+    m = DistilWhisperB200ForConditionalGeneration(dims.to_dict())
+    m.load_hf_state_dict({k: v.clone() for k, v in sd.items()})
+    m = m.to("cuda", dtype)
+    if freeze_encoder:
+        for p in m.model.encoder.parameters():
+            p.requires_grad = False
+    return m
+
+
+def _cuda(batch):
+    return {k: v.cuda() for k, v in batch.items()}
+
+
+def test_state_dict_names_match_hf_layout():
+    sc = wo.PRESETS["tiny-student"]
+    m = _build(sc, wo.init_state_dict(sc, 1))
+    ours = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    expected = {k: tuple(v) for k, v in wo.param_shapes(sc).items()}
+    expected["proj_out.weight"] = expected["model.decoder.embed_tokens.weight"]
+    assert ours == expected
+    assert m.proj_out.weight.data_ptr() == m.model.decoder.embed_tokens.weight.data_ptr()
+    names = [n for n, _ in m.named_parameters()]
+    assert "proj_out.weight" not in names and "model.decoder.embed_tokens.weight" in names   # tied weight listed once
+
+
+def test_tiny_kd_step_matches_hf_golden(golden_dir):
+    """Branch B (frozen + shared encoder, the reference recipe): loss / logits / grads vs HF golden."""
+    from distil_whisper_b200.kd import DistillationStep
+    g = np.load(os.path.join(golden_dir, "kd_tiny.npz"))
+    s_seed, t_seed, b_seed = [int(x) for x in g["seeds"]]
+    sc, tc = wo.PRESETS["tiny-student"], wo.PRESETS["tiny-teacher"]
+    ssd, tsd = wo.init_state_dict(sc, s_seed), wo.init_state_dict(tc, t_seed)
+    student = _build(sc, ssd, freeze_encoder=True)
+    teacher = _build(tc, tsd, dtype=torch.bfloat16)
+    step = DistillationStep(student, teacher, kl_weight=1.0, keep_logits=True)
+    assert step.share_hidden_states and teacher.model.encoder is student.model.encoder
+    batch = _cuda(wo.synthetic_batch(sc, batch=3, n_tok=12, seed=b_seed))
+    loss, metrics = step.train_step(batch, temperature=2.0)
+    loss.backward()
+    assert abs(loss.item() - float(g["B_loss"])) / float(g["B_loss"]) < LOSS_REL
+    assert abs(metrics["ce_loss"].item() - float(g["B_ce_loss"])) / float(g["B_ce_loss"]) < LOSS_REL
+    # the teacher runs in bf16 weights (reference: teacher_dtype bf16) -> KL itself is a small number; 5% of it
+    assert abs(metrics["kl_loss"].item() - float(g["B_kl_loss"])) / float(g["B_kl_loss"]) < 5e-2
+    assert _rel(step.last_student_logits, g["B_student_logits"]) < LOGITS_REL
+    assert _rel(step.last_teacher_logits, g["B_teacher_logits"]) < 2 * LOGITS_REL
+    enc = step.last_encoder_states.float().view(3, -1, sc.d_model)
+    assert _rel(enc, g["B_encoder_last_hidden_state"]) < LOGITS_REL
+    # token-id argmax: exact except where the fp32 top-2 margin is inside the bf16 tolerance
+    ref_logits = torch.from_numpy(g["B_student_logits"])
+    top2 = ref_logits.topk(2, dim=-1).values
+    safe = (top2[..., 0] - top2[..., 1]) > 4 * LOGITS_REL * ref_logits.abs().max()
+    ours = step.last_student_logits.float().cpu().argmax(-1)
+    assert (ours[safe] == ref_logits.argmax(-1)[safe]).all()
+    names = [str(n) for n in g["B_grad_names"]]
+    got = {n for n, p in student.named_parameters() if p.grad is not None and p.requires_grad}
+    assert got == set(names), (sorted(got ^ set(names)))
+    params = dict(student.named_parameters())
+    worst = 0.0
+    for n, norm in zip(names, g["B_grad_norms"]):
+        gr = params[n].grad
+        assert abs(float(gr.norm()) - norm) / (norm + 1e-12) < GRAD_REL, (n, float(gr.norm()), norm)
+        key = f"B_grad::{n}"
+        if key in g.files:
+            r = _rel(gr, g[key])
+            worst = max(worst, r)
+            assert r < GRAD_REL, (n, r)
+    print("worst grad rel err", worst)
+    assert float(student.model.decoder.embed_tokens.weight.grad[sc.pad_token_id].abs().sum()) > 0
+
+
+def test_generic_forward_backward_path_matches_oracle():
+    """model(**batch).loss.backward() -- the un-fused HF-shaped path (CE only) -- against the fp32 oracle."""
+    sc = wo.PRESETS["tiny-student"]
+    ssd = wo.init_state_dict(sc, 3)
+    student = _build(sc, ssd, freeze_encoder=True)
+    batch = wo.synthetic_batch(sc, batch=2, n_tok=9, seed=4)
+    out = student(**_cuda(batch))
+    assert out.logits.shape == (2, 9, sc.vocab_size) and out.encoder_last_hidden_state.shape == (2, 50, sc.d_model)
+    out.loss.backward()
+    osd = {k: v.clone().requires_grad_(k.startswith("model.decoder")) for k, v in ssd.items()}
+    ref = wo.model_forward(osd, sc, **batch)
+    ref["loss"].backward()
+    assert abs(out.loss.item() - ref["loss"].item()) / ref["loss"].item() < LOSS_REL
+    assert _rel(out.logits, ref["logits"].detach()) < LOGITS_REL
+    for n, p in student.named_parameters():
+        if p.requires_grad:
+            assert _rel(p.grad, osd[n].grad) < GRAD_REL, n
+    # labels only -> decoder inputs built by shift_tokens_right (teacher call shape, ref :1477-1478)
+    with torch.no_grad():
+        out2 = student(encoder_outputs=(out.encoder_last_hidden_state,), labels=batch["labels"].cuda())
+        ref2 = wo.model_forward(ssd, sc, labels=batch["labels"], encoder_hidden_states=ref["encoder_last_hidden_state"].detach())
+    assert _rel(out2.logits, ref2["logits"]) < LOGITS_REL
+    with pytest.raises(ValueError):
+        student(input_features=torch.zeros(1, sc.num_mel_bins, 98, device="cuda"), decoder_input_ids=batch["decoder_input_ids"][:1].cuda())
+
+
+def test_plumbing_config_small_en_vs_oracle():
+    """BASELINE.json configs[0]: distil-small.en-shaped student (12/4/768) + 12/12 teacher, 2 x (80 x 3000), 32 labels."""
+    from distil_whisper_b200.kd import DistillationStep
+    sc, tc = wo.PRESETS["distil-small.en"], wo.PRESETS["small.en-teacher"]
+    ssd, tsd = wo.init_state_dict(sc, 5), wo.init_state_dict(tc, 6)
+    for k in list(tsd):
+        if k.startswith("model.encoder."):
+            tsd[k] = ssd[k]
+    batch = wo.synthetic_batch(sc, batch=2, n_tok=32, seed=7)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    for k, v in ssd.items():
+        v.requires_grad_(k.startswith("model.decoder"))
+    loss_ref, m_ref, so, to = wo.kd_train_step(ssd, sc, tsd, tc, batch, 2.0, 1.0, share_hidden_states=True)
+    loss_ref.backward()
+    student = _build(sc, {k: v.detach() for k, v in ssd.items()}, freeze_encoder=True)
+    teacher = _build(tc, tsd, dtype=torch.bfloat16)
+    step = DistillationStep(student, teacher, keep_logits=True)
+    loss, metrics = step.train_step(_cuda(batch), temperature=2.0)
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) / loss_ref.item() < LOSS_REL, (loss.item(), loss_ref.item())
+    assert _rel(step.last_student_logits, so["logits"].detach()) < LOGITS_REL
+    bad = []
+    for n, p in student.named_parameters():
+        if p.requires_grad:
+            r = _rel(p.grad, ssd[n].grad)
+            # softmax-logit gradients (q / k projections) go through the P * (dP - delta) cancellation: 2x looser in bf16
+            tol = 2 * GRAD_REL if (".q_proj." in n or ".k_proj." in n) else GRAD_REL
+            if r > tol:
+                bad.append((n, r))
+    assert not bad, bad
+
+
+def test_fused_adamw_and_second_step_changes_loss():
+    from distil_whisper_b200.kd import DistillationStep
+    from distil_whisper_b200.optim import FusedAdamW
+    sc, tc = wo.PRESETS["tiny-student"], wo.PRESETS["tiny-teacher"]
+    student = _build(sc, wo.init_state_dict(sc, 11), freeze_encoder=True)
+    teacher = _build(tc, wo.init_state_dict(tc, 23), dtype=torch.bfloat16)
+    step = DistillationStep(student, teacher)
+    opt = FusedAdamW.for_model(student, lr=1e-3, weight_decay=0.01, max_grad_norm=1.0)
+    assert len(opt.param_groups) == 2
+    n_decay = sum(p.numel() for p in opt.param_groups[0]["params"])
+    n_nodecay = sum(p.numel() for p in opt.param_groups[1]["params"])
+    assert n_decay > n_nodecay > 0
+    batch = _cuda(wo.synthetic_batch(sc, batch=3, n_tok=12, seed=5))
+    losses = []
+    for _ in range(4):
+        loss, _ = step.train_step(batch, 2.0)
+        loss.backward()
+        opt.all_reduce_gradients()
+        opt.step()
+        opt.zero_grad()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0], losses
+    assert float(opt.flat.grad.abs().sum()) == 0.0
