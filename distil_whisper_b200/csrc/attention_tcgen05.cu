@@ -3,8 +3,9 @@
 //   S = Q K^T      tcgen05.mma 128x128x64  (Q, K tiles: TMA, 128B swizzle, K-major)        -> TMEM cols [0,128)
 //   softmax        one thread per query row (tcgen05.ld 32x32b: lane == row, no shuffles), online max/sum in fp32,
 //                  P (bf16) written to a swizzled smem tile
-//   O_j = P V      tcgen05.mma 128x64x128  (V tile is the MN-major B operand: no transpose)  -> TMEM cols [128,192)
-//   O  += O_j      folded into registers with the running-max correction, normalised at the end, TMA store
+//   O += P V       tcgen05.mma 128x64x128  (V tile is the MN-major B operand: no transpose)  -> TMEM cols [128,192),
+//                  accumulated in TMEM across key tiles; rescaled (tcgen05.ld/st) only when a row maximum grows by > 2^8
+//                  ("lazy rescale"), normalised by the row sum at the end, TMA store
 // Two CTAs are resident per SM (112 KB smem, 256 TMEM columns each), so one CTA's exp2-bound softmax overlaps the
 // other's MMAs; inside a CTA, QK^T of tile j+1 is issued as soon as tile j's scores have left TMEM.
 //
@@ -15,7 +16,7 @@
 namespace dwb {
 
 constexpr int TA_BQ = 128, TA_BK = 128, TA_HD = 64;
-constexpr int TA_THREADS = 192;
+constexpr int TA_THREADS = 256;   // warps 0-3 softmax warpgroup; warp 4 TMA, warp 5 MMA, warps 6-7 idle (complete the 2nd warpgroup)
 constexpr int TA_TILE_BYTES = 128 * 128;            // 128 rows x 128 B
 constexpr int TA_TILES_BYTES = TA_TILE_BYTES /*Q*/ + 2 * 2 * TA_TILE_BYTES /*K,V x 2 stages*/ + 2 * TA_TILE_BYTES /*P*/;
 constexpr int TA_BAR_BYTES = 96;
@@ -74,7 +75,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
     mbar_init(s_full, 1); mbar_init(s_empty, 128);
     mbar_init(p_full, 128); mbar_init(p_empty, 1);
-    mbar_init(o_full, 1); mbar_init(o_empty, 128);
+    mbar_init(o_full, 1); mbar_init(o_empty, 128);   // o_empty unused since O accumulates in TMEM
     fence_barrier_init();
   }
   if (warp == 5) {
@@ -88,113 +89,133 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const uint32_t tmem_s = tmem_base;            // 128 columns of scores
   const uint32_t tmem_o = tmem_base + 128;      // 64 columns: P V of the current tile
 
+  // register re-distribution between the two warpgroups (launch: 128/thread for 2 CTAs/SM): 208 for softmax, 48 for the rest
+  if (warp >= 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+  }
   if (warp == 4) {
-    // ===================================== TMA producer =====================================
+    // ===================================== TMA producer (one thread) ========================
     if (lane == 0) {
       mbar_expect_tx(q_full, TA_TILE_BYTES);
       tma_load_3d(&tmap_q, q_full, sQ, h * TA_HD, q0, b);
-    }
-    for (int j = 0; j < n_kv; ++j) {
-      const int st = j & 1;
-      mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-      if (lane == 0) {
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(&kv_full[st], 2 * TA_TILE_BYTES);
         tma_load_3d(&tmap_k, &kv_full[st], sKV + st * 2 * TA_TILE_BYTES, h * TA_HD, j * TA_BK, b);
         tma_load_3d(&tmap_v, &kv_full[st], sKV + st * 2 * TA_TILE_BYTES + TA_TILE_BYTES, h * TA_HD, j * TA_BK, b);
       }
-      __syncwarp();
     }
+    __syncwarp();
   } else if (warp == 5) {
-    // ===================================== MMA issuer =======================================
-    constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
-    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
-    mbar_wait(q_full, 0);
-    const uint64_t dq = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-    for (int j = 0; j < n_kv; ++j) {
-      const int st = j & 1;
-      mbar_wait(&kv_full[st], (j >> 1) & 1);
-      mbar_wait(s_empty, (j & 1) ^ 1);
-      tc_fence_after();
-      if (lane == 0) {
+    // ===================================== MMA issuer (one thread) ==========================
+    // issue order: QK(0), then per tile j: QK(j+1) (as soon as tile j's scores have left TMEM), PV(j) (once P_j is in smem)
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
+      mbar_wait(q_full, 0);
+      const uint64_t dq = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+      const uint64_t dp0 = umma_desc_sw128(smem_u32(sP), 16, 1024);
+      auto issue_qk = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        mbar_wait(s_empty, (j & 1) ^ 1);
+        tc_fence_after();
         const uint64_t dk = umma_desc_sw128(smem_u32(sKV + st * 2 * TA_TILE_BYTES), 16, 1024);
 #pragma unroll
         for (int k = 0; k < TA_HD / 16; ++k) tc_mma_ss(tmem_s, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_qk, k > 0 ? 1u : 0u);
         tc_commit(s_full);
-      }
-      __syncwarp();
-      mbar_wait(p_full, j & 1);
-      mbar_wait(o_empty, (j & 1) ^ 1);
-      tc_fence_after();
-      if (lane == 0) {
+      };
+      issue_qk(0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        if (j + 1 < n_kv) issue_qk(j + 1);
+        mbar_wait(p_full, j & 1);                  // P_j written (and any rescale of O finished)
+        tc_fence_after();
         const uint64_t dv = umma_desc_sw128(smem_u32(sKV + st * 2 * TA_TILE_BYTES + TA_TILE_BYTES), TA_TILE_BYTES, 1024);
 #pragma unroll
         for (int k = 0; k < TA_BK / 16; ++k) {
-          const uint64_t dp = umma_desc_sw128(smem_u32(sP + (k >> 2) * TA_TILE_BYTES), 16, 1024) + (uint64_t)(2 * (k & 3));
-          tc_mma_ss(tmem_o, dp, dv + (uint64_t)(k * 128), idesc_pv, k > 0 ? 1u : 0u);
+          const uint64_t dp = dp0 + (uint64_t)((k >> 2) * (TA_TILE_BYTES >> 4) + 2 * (k & 3));
+          tc_mma_ss(tmem_o, dp, dv + (uint64_t)(k * 128), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);   // O accumulates in TMEM
         }
         tc_commit(o_full);
         tc_commit(&kv_empty[st]);
         tc_commit(p_empty);
       }
-      __syncwarp();
     }
-  } else {
+    __syncwarp();
+  } else if (warp < 4) {
     // ===================================== softmax / output =================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    // One thread per query row.  O lives in TMEM and is only rescaled when the row maximum has grown by more than 2^8
+    // relative to the reference maximum m_ref the accumulators are expressed in (bf16 P and fp32 sums absorb the 2^8).
     const int row = warp * 32 + lane;                       // query row of this thread == TMEM lane
     const uint32_t t_s = tmem_s + ((uint32_t)(warp * 32) << 16);
     const uint32_t t_o = tmem_o + ((uint32_t)(warp * 32) << 16);
     const uint32_t sP_row = smem_u32(sP) + row * 128;
     const int sw = row & 7;
-    float m_run = -INFINITY, l_run = 0.f, m_prev = -INFINITY, m_ref = -INFINITY;
-    float o_acc[TA_HD];
-#pragma unroll
-    for (int i = 0; i < TA_HD; ++i) o_acc[i] = 0.f;
+    float m_ref = -INFINITY, l_run = 0.f;
 
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int kbase = j * TA_BK;
       const bool tail = kbase + TA_BK > p.Sk;
-      // pass 1: row max
-      float mx = m_run;
+      uint32_t v[128];
+      tmem_ld_32x32(t_s, v);
+      tmem_ld_32x32(t_s + 32, v + 32);
+      tmem_ld_32x32(t_s + 64, v + 64);
+      tmem_ld_32x32(t_s + 96, v + 96);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_empty);                                 // scores are in registers: QK^T of the next tile may start
+      if (tail) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_s + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(v[i]);
-          if (tail && kbase + c * 32 + i >= p.Sk) s = -INFINITY;
-          mx = fmaxf(mx, s);
-        }
+        for (int i = 0; i < 128; ++i)
+          if (kbase + i >= p.Sk) v[i] = __float_as_uint(-INFINITY);
       }
-      const float m_new = mx;                               // finite: every tile holds at least one valid key
-      const float msc = m_new * p.scale_log2;
-      const float corr = (m_run == -INFINITY) ? 0.f : exp2f(m_run * p.scale_log2 - msc);
-      l_run *= corr;
+      // row max with 8 independent chains (a single fmaxf chain would serialise 128 dependent 4-cycle ops)
+      float mxp[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) mxp[c] = __uint_as_float(v[c]);
+#pragma unroll
+      for (int i = 8; i < 128; i += 8) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) mxp[c] = fmaxf(mxp[c], __uint_as_float(v[i + c]));
+      }
+      const float mx = fmaxf(fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3])), fmaxf(fmaxf(mxp[4], mxp[5]), fmaxf(mxp[6], mxp[7])));
+      if (j == 0) {
+        m_ref = mx;
+      } else if ((mx - m_ref) * p.scale_log2 > 8.0f) {
+        // rare: bring O (TMEM) and l to the new reference maximum.  P V of tile j-1 must have landed first.
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+        const float f = fast_exp2((m_ref - mx) * p.scale_log2);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t o[32];
+          tmem_ld_32x32(t_o + c * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+          tmem_st_32x32(t_o + c * 32, o);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        l_run *= f;
+        m_ref = mx;
+      }
+      const float msc = m_ref * p.scale_log2;
       mbar_wait(p_empty, (j & 1) ^ 1);                      // P V of the previous tile has consumed sP
-      // pass 2: p = exp2(s * scale_log2 - m * scale_log2), row sum, bf16 pack into the swizzled P tile
-      float lsum = 0.f;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};          // independent partial sums (no 128-long dependent FADD chain)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_s + c * 32, v);
-        tmem_ld_wait();
-        if (c == 3) {                                       // scores fully read: QK^T of the next tile may overwrite
-          tc_fence_before();
-          mbar_arrive(s_empty);
-        }
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float e0 = exp2f(__uint_as_float(v[i]) * p.scale_log2 - msc);
-          float e1 = exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - msc);
-          if (tail) {
-            if (kbase + c * 32 + i >= p.Sk) e0 = 0.f;
-            if (kbase + c * 32 + i + 1 >= p.Sk) e1 = 0.f;
-          }
-          lsum += e0 + e1;
+          const float e0 = fast_exp2(fmaf(__uint_as_float(v[c * 32 + i]), p.scale_log2, -msc));
+          const float e1 = fast_exp2(fmaf(__uint_as_float(v[c * 32 + i + 1]), p.scale_log2, -msc));
+          ls[(i >> 1) & 3] += e0 + e1;
           pk[i >> 1] = pack_bf16x2(e0, e1);
         }
         const uint32_t half = sP_row + (c >> 1) * TA_TILE_BYTES;
@@ -204,52 +225,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           st_shared_v4(half + ((chunk ^ sw) << 4), pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
         }
       }
-      l_run += lsum;
+      l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       fence_proxy_async_smem();
       mbar_arrive(p_full);
-      // fold the previous tile's P V (computed against m_prev) into the register accumulator
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
-        tc_fence_after();
-        const float f = (m_ref == -INFINITY) ? 0.f : exp2f((m_ref - m_prev) * p.scale_log2);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_o + c * 32, v);
-          tmem_ld_wait();
-          if (c == 1) {
-            tc_fence_before();
-            mbar_arrive(o_empty);
-          }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], f, __uint_as_float(v[i]));
-        }
-        m_ref = m_prev;
-      }
-      m_prev = m_new;
-      m_run = m_new;
     }
-    // last tile's P V
-    {
-      mbar_wait(o_full, (n_kv - 1) & 1);
-      tc_fence_after();
-      const float f = (m_ref == -INFINITY) ? 0.f : exp2f((m_ref - m_prev) * p.scale_log2);
-      const float inv = 1.f / l_run;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_o + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], f, __uint_as_float(v[i])) * inv;
-      }
-    }
-    // output tile through sQ (Q is dead: every QK^T has completed) -> TMA store clips rows >= Sq
+    // epilogue: O / l  ->  bf16 tile through sQ (Q is dead: every QK^T has completed) -> TMA store clips rows >= Sq
+    mbar_wait(o_full, (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.f / l_run;
     const uint32_t sO_row = smem_u32(sQ) + row * 128;
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch)
-      st_shared_v4(sO_row + ((ch ^ sw) << 4), pack_bf16x2(o_acc[ch * 8], o_acc[ch * 8 + 1]), pack_bf16x2(o_acc[ch * 8 + 2], o_acc[ch * 8 + 3]),
-                   pack_bf16x2(o_acc[ch * 8 + 4], o_acc[ch * 8 + 5]), pack_bf16x2(o_acc[ch * 8 + 6], o_acc[ch * 8 + 7]));
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32(t_o + c * 32, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const float* f = reinterpret_cast<const float*>(o) + ch * 8;
+        st_shared_v4(sO_row + (((c * 4 + ch) ^ sw) << 4), pack_bf16x2(f[0] * inv, f[1] * inv), pack_bf16x2(f[2] * inv, f[3] * inv),
+                     pack_bf16x2(f[4] * inv, f[5] * inv), pack_bf16x2(f[6] * inv, f[7] * inv));
+      }
+    }
     fence_proxy_async_smem();
     named_bar_sync(1, 128);
     if (threadIdx.x == 0) {
@@ -258,7 +254,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       tma_store_wait_all<0>();
     }
     if (p.lse != nullptr && q0 + row < p.Sq)
-      p.lse[((int64_t)b * p.H + h) * p.Sq + q0 + row] = m_run * p.scale + __logf(l_run);
+      p.lse[((int64_t)b * p.H + h) * p.Sq + q0 + row] = m_ref * p.scale + __logf(l_run);
   }
 
   tc_fence_before();

@@ -36,7 +36,8 @@ class _Cache:
 
     @staticmethod
     def _key(params):
-        return tuple((p.data_ptr(), p._version, p.dtype, _PARAM_EPOCH[0] if p.requires_grad else 0)
+        # the epoch only concerns fp32 masters that optim.FusedAdamW rewrites through raw pointers
+        return tuple((p.data_ptr(), p._version, p.dtype, _PARAM_EPOCH[0] if (p.requires_grad and p.dtype == F32) else 0)
                      for p in params if p is not None)
 
     def get(self, name, params, build):
@@ -264,7 +265,7 @@ def decoder_forward(st: _State, ids, enc, B, S, save):
         x2, h2, mu2, rs2 = ops.add_layernorm(x1, y1, g, b_, rows=M, d=d, save_stats=save)
         qc = ops.gemm(h2, wc["wq"], bias=wc["bq"])
         kvc = ops.gemm(enc, wc["wkv"], bias=wc["bkv"])                                  # [B*S, 2d]
-        o2, lse2 = ops.attention_fwd(qc, kvc[:, :d], kvc[:, d:], B, H, T, S, causal=False, need_lse=save)
+        o2, lse2 = ops.attention_fwd(qc, kvc[:, :d], kvc[:, d:], B, H, T, S, causal=False, need_lse=save, use_tc=USE_TC_ATTENTION)
         y2 = ops.gemm(o2, wc["wo"], bias=wc["bo"])
         # --- MLP
         g, b_ = _ln(st, k + ".ln3", layer.final_layer_norm)

@@ -62,6 +62,10 @@ class _KDStepFn(torch.autograd.Function):
         return None, None, None, None, None
 
 
+class _PlainCtx:
+    """Stand-in for the autograd ctx when forward and backward are issued back to back without autograd (CUDA graph)."""
+
+
 class DistillationStep:
     """Holds the student / teacher pair the way the reference's closures capture them (ref :1449, :1046-1049)."""
 
@@ -94,8 +98,65 @@ class DistillationStep:
         return loss, {"loss": loss, "ce_loss": m[1], "kl_loss": m[2]}
 
     @torch.no_grad()
+    def forward_backward(self, batch, temperature: float = 2.0, loss_scale: float = 1.0):
+        """train_step + loss.backward() as one straight-line kernel sequence (no autograd graph): gradients are accumulated
+        into .grad exactly as loss.backward() would.  This is what GraphedDistillationStep captures."""
+        self.student.train()
+        self.teacher.eval()
+        engine._check_trainable_dtypes(self.student)
+        if any(p.requires_grad for n, p in self.student.model.encoder.named_parameters() if "embed_positions" not in n):
+            raise NotImplementedError("trainable student encoder (variant A) is not built yet; use the --freeze_encoder recipe")
+        ctx = _PlainCtx()
+        loss, m = _KDStepFn.forward(ctx, self, batch, float(temperature), float(loss_scale), None)
+        engine.decoder_backward(engine.state_of(self.student.model.decoder), ctx.dctx, ctx.dl)
+        return loss, {"loss": loss, "ce_loss": m[1], "kl_loss": m[2]}
+
+    @torch.no_grad()
     def eval_step(self, batch):
         self.student.eval()
         self.teacher.eval()
         _, m = _KDStepFn.forward(None, self, batch, 1.0, 1.0, None)
         return {"loss": m[0], "ce_loss": m[1], "kl_loss": m[2]}
+
+
+class GraphedDistillationStep:
+    """`train_step` + `loss.backward()` captured once into a CUDA graph and replayed per batch.
+
+    The KD step issues ~6000 kernel launches with fixed shapes; replaying them as one graph removes the per-launch host
+    cost (ctypes call, tensor-map encode, allocator) from the critical path.  Batches are copied into static device
+    buffers; parameter gradients land in the same (flat) buffers as in the eager path, so the optimiser and the gradient
+    all-reduce are unchanged and stay outside the graph (their scalars change every step)."""
+
+    def __init__(self, step: DistillationStep, example_batch: dict, temperature: float = 2.0, loss_scale: float = 1.0, warmup: int = 2):
+        self.step = step
+        self.static_batch = {k: v.clone() for k, v in example_batch.items()}
+        params = [p for p in step.student.parameters() if p.requires_grad]
+        if any(p.grad is None for p in params):
+            raise RuntimeError("bind the gradients to static buffers first (construct optim.FusedAdamW before graph capture)")
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            saved = [p.grad.clone() for p in params]
+            for _ in range(warmup):                       # builds shadows / sets kernel attributes outside the capture
+                step.forward_backward(self.static_batch, temperature, loss_scale)
+            for p, g in zip(params, saved):
+                p.grad.copy_(g)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        # the bf16 shadows of trainable weights must be re-cast on every replay: invalidate them so that the cast kernels
+        # are part of the captured work (frozen weights keep their cached shadows and are not re-cast)
+        engine.bump_param_epoch()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            loss, metrics = step.forward_backward(self.static_batch, temperature, loss_scale)
+            self.loss = loss
+            self.metrics = metrics
+
+    def __call__(self, batch: dict | None = None):
+        """Copy `batch` (device or pinned host tensors) into the static buffers, replay, return (loss, metrics) tensors that
+        are overwritten by the next call.  Gradients are ACCUMULATED into .grad exactly like loss.backward()."""
+        if batch is not None:
+            for k, dst in self.static_batch.items():
+                dst.copy_(batch[k], non_blocking=True)
+        self.graph.replay()
+        return self.loss, self.metrics

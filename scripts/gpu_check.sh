@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,driver_version,memory.total --format=csv > gpurun_ou
 rc=0
 for t in "$@"; do
   name=$(basename "$t" .py)
-  timeout 900 python -m pytest "$t" -q -m gpu -p no:cacheprovider > "gpurun_out/${name}.log" 2>&1
+  timeout ${DWB_TEST_TIMEOUT:-420} python -m pytest "$t" -q -m gpu -p no:cacheprovider --durations=6 > "gpurun_out/${name}.log" 2>&1
   code=$?
   echo "$name exit=$code" | tee -a gpurun_out/summary.txt
   tail -n 25 "gpurun_out/${name}.log"

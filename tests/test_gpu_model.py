@@ -177,3 +177,31 @@ def test_fused_adamw_and_second_step_changes_loss():
         losses.append(loss.item())
     assert losses[-1] < losses[0], losses
     assert float(opt.flat.grad.abs().sum()) == 0.0
+
+
+def test_cuda_graph_replay_matches_eager():
+    """GraphedDistillationStep (fwd + loss + bwd as one CUDA graph) == train_step + loss.backward(), across weight updates."""
+    from distil_whisper_b200.kd import DistillationStep, GraphedDistillationStep
+    from distil_whisper_b200.optim import FusedAdamW
+    sc, tc = wo.PRESETS["tiny-student"], wo.PRESETS["tiny-teacher"]
+
+    def make():
+        student = _build(sc, wo.init_state_dict(sc, 11), freeze_encoder=True)
+        teacher = _build(tc, wo.init_state_dict(tc, 23), dtype=torch.bfloat16)
+        step = DistillationStep(student, teacher)
+        return step, FusedAdamW.for_model(student, lr=1e-3, max_grad_norm=1.0)
+    b1 = _cuda(wo.synthetic_batch(sc, batch=3, n_tok=12, seed=5))
+    b2 = _cuda(wo.synthetic_batch(sc, batch=3, n_tok=12, seed=6))
+    step_e, opt_e = make()
+    step_g, opt_g = make()
+    graphed = GraphedDistillationStep(step_g, b1, temperature=2.0)
+    assert float(opt_g.flat.grad.abs().sum()) == 0.0          # capture and warm-up left no gradient behind
+    for batch in (b1, b2, b1):
+        le, _ = step_e.train_step(batch, 2.0)
+        le.backward()
+        lg, _ = graphed(batch)
+        assert abs(le.item() - lg.item()) < 1e-6 * abs(le.item()) + 1e-7
+        assert _rel(opt_g.flat.grad, opt_e.flat.grad) < 2e-4          # fp32 atomics order only (dQ, LN/bias column sums)
+        opt_e.step()
+        opt_g.step()
+    assert _rel(opt_g.flat.data, opt_e.flat.data) < 1e-5
