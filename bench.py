@@ -33,6 +33,8 @@ BATCH, N_TOK = 32, 128
 # algorithmic FLOPs per utterance of the frozen-encoder recipe (variant B of BASELINE.md section 2): encoder fwd once,
 # teacher decoder + LM head fwd, student decoder + LM head fwd + bwd (2x)
 TF_PER_UTT_B = (2272.7 + 553.6 + 3 * 50.5) / 1e3
+# variant A: trainable student encoder (fwd + bwd = 3x) and a separate teacher encoder forward
+TF_PER_UTT_A = (3 * (2272.7 + 50.5) + 2272.7 + 553.6) / 1e3
 
 
 def synthetic_batch(batch, n_tok, seed, dims, device="cpu"):
@@ -118,15 +120,16 @@ def run_reference(args):
         "gpu_launches": 0, "loss": loss}))
 
 
-def build_models(device):
+def build_models(device, variant="B"):
     from distil_whisper_b200.modeling import DistilWhisperB200ForConditionalGeneration
     torch.manual_seed(0)
     with torch.device(device):
         student = DistilWhisperB200ForConditionalGeneration(STUDENT)
         teacher = DistilWhisperB200ForConditionalGeneration(TEACHER)
     teacher = teacher.to(torch.bfloat16)                                   # ref :985-992 teacher_dtype bf16
-    for p in student.model.encoder.parameters():                          # ref :1023-1026 --freeze_encoder
-        p.requires_grad = False
+    if variant == "B":
+        for p in student.model.encoder.parameters():                      # ref :1023-1026 --freeze_encoder
+            p.requires_grad = False
     return student, teacher
 
 
@@ -139,6 +142,9 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2, help="utterances per CPU reference step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
+    ap.add_argument("--variant", default="B", choices=["A", "B"],
+                    help="B: frozen + shared encoder (reference README / paper recipe, default).  A: trainable student encoder, "
+                         "separate teacher encoder (BASELINE.md section 2)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -152,7 +158,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     _abi.call("dwb_check_device")
-    student, teacher = build_models(dev)
+    student, teacher = build_models(dev, args.variant)
+    tf_per_utt = TF_PER_UTT_B if args.variant == "B" else TF_PER_UTT_A
     ddp.broadcast_parameters(student)
     ddp.broadcast_parameters(teacher)
     step = DistillationStep(student, teacher, kl_weight=1.0)
@@ -239,16 +246,17 @@ def main():
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "configs[1]: distil-large-v3 student + large-v3 teacher KD step (fwd student+teacher, fused CE+KL, "
-                               "bwd, grad all-reduce, clip, AdamW), frozen+shared encoder = README/paper recipe (BASELINE.md variant B), "
+                               "bwd, grad all-reduce, clip, AdamW), " + ("frozen+shared encoder = README/paper recipe (BASELINE.md variant B), " if args.variant == "B"
+                               else "trainable student encoder + separate teacher encoder (BASELINE.md variant A), ") +
                                f"{BATCH}x(80x3000 mel, {N_TOK} tok) per GPU", "global_batch": utt, "seq_len": N_TOK,
-                   "parallelism": f"dp{world}", "l2": "working set >> 126 MB L2, no flush", "variant": "B (--freeze_encoder)",
-                   "algorithmic_tflop_per_utt": TF_PER_UTT_B},
+                   "parallelism": f"dp{world}", "l2": "working set >> 126 MB L2, no flush", "variant": "B (--freeze_encoder)" if args.variant == "B" else "A (trainable encoder)",
+                   "algorithmic_tflop_per_utt": tf_per_utt},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "gemm_bf16_tcgen05_kernel (all launches of the timed region)",
                      "peak_source": peak_src, "gemm_share_of_step": gemm_ms * 1e-3 / args.steps / sec_eager if sec_eager > 0 else None,
                      "measured_in": "eager replay of the same steps (ms_per_step_eager below)",
                      "gemm_launches": len(prof)},
-        "step_roofline": {"achieved_tflops_per_gpu": utt / sec * TF_PER_UTT_B / world, "frac_of_peak": utt / sec * TF_PER_UTT_B / world / peak},
+        "step_roofline": {"achieved_tflops_per_gpu": utt / sec * tf_per_utt / world, "frac_of_peak": utt / sec * tf_per_utt / world / peak},
         "e2e": {"value": utt / sec_e2e, "unit": "utterances/s",
                 "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host_batch.values()), "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "clocks": clocks, "loss": final_loss, "ms_per_step_eager": sec_eager * 1e3,

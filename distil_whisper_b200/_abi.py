@@ -35,6 +35,7 @@ SIGNATURES = {
     "dwb_conv_wgrad_kc_to_ck": (_i, [_p, _p, _i, _i, _i, _p]),
     "dwb_im2col_conv1": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "dwb_im2col_conv2": (_i, [_p, _p, _i, _i, _i, _p]),
+    "dwb_col2im_conv2_gelu_bwd": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "dwb_embed_fwd": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p]),
     "dwb_embed_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "dwb_colsum_bf16": (_i, [_p, _l, _p, _i, _i, _i, _p]),

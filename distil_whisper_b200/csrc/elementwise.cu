@@ -459,3 +459,55 @@ extern "C" int dwb_gelu_fwd(const void* h, void* y, int64_t n, void* stream) {
   DWB_LAUNCH_OK();
   return DWB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// conv2 input gradient: col2im of the im2col-space gradient g [B*L/2, 3*d] (column k*d + c) back onto the channels-last
+// conv1 activation grid [B, L, d], fused with conv1's GELU backward:  dpre1 = col2im(g) * gelu'(pre1).
+// Position p receives tap k=1 of output t=p/2 (p even) or taps k=0 of t=(p+1)/2 and k=2 of t=(p-1)/2 (p odd).
+namespace dwb {
+__global__ void col2im_conv2_gelu_bwd_kernel(const bf16* __restrict__ g, const bf16* __restrict__ pre1, bf16* __restrict__ out, int B,
+                                             int L, int d) {
+  const int Lo = L / 2;
+  const int vec = d / 8;
+  const int64_t n = (int64_t)B * L * vec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % vec) * 8;
+    const int64_t row = i / vec;
+    const int p = (int)(row % L), b = (int)(row / L);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    auto add = [&](int t, int k) {
+      if (t < 0 || t >= Lo) return;
+      const uint4 u = *reinterpret_cast<const uint4*>(g + ((int64_t)b * Lo + t) * 3 * d + (int64_t)k * d + c);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        acc[2 * j] += f.x; acc[2 * j + 1] += f.y;
+      }
+    };
+    if ((p & 1) == 0) {
+      add(p >> 1, 1);
+    } else {
+      add((p + 1) >> 1, 0);
+      add((p - 1) >> 1, 2);
+    }
+    const uint4 pu = *reinterpret_cast<const uint4*>(pre1 + row * d + c);
+    const uint32_t pw[4] = {pu.x, pu.y, pu.z, pu.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x = unpack_bf16x2(pw[j]);
+      o[j] = pack_bf16x2(acc[2 * j] * gelu_erf_grad(x.x), acc[2 * j + 1] * gelu_erf_grad(x.y));
+    }
+    *reinterpret_cast<uint4*>(out + row * d + c) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+}  // namespace dwb
+
+extern "C" int dwb_col2im_conv2_gelu_bwd(const void* g_bf16, const void* pre1_bf16, void* out_bf16, int B, int L, int d, void* stream) {
+  DWB_CHECK_ARG(g_bf16 && pre1_bf16 && out_bf16 && B > 0 && L > 0 && (L % 2) == 0 && (d % 8) == 0, "dwb_col2im_conv2_gelu_bwd: bad args");
+  dwb::col2im_conv2_gelu_bwd_kernel<<<dwb::grid_for((int64_t)B * L * (d / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)g_bf16, (const bf16*)pre1_bf16, (bf16*)out_bf16, B, L, d);
+  DWB_LAUNCH_OK();
+  return DWB_OK;
+}

@@ -171,15 +171,34 @@ def _ln(st, key, ln):
 USE_TC_ATTENTION = True     # tcgen05 encoder attention (attention_tcgen05.cu); False -> mma.sync kernel
 
 
+def _conv1_w(st, ld):
+    enc = st.m
+    d, C = enc.conv1.weight.shape[0], enc.conv1.weight.shape[1]
+
+    def build(old):
+        w = torch.zeros((d, ld), dtype=BF16, device=enc.conv1.weight.device) if old is None else old
+        _to_bf16(w[:, :3 * C], enc.conv1.weight)
+        return w
+    return st.cache.get("conv1.w", [enc.conv1.weight], build)
+
+
+def _conv2_w(st):
+    enc = st.m
+
+    def build(old):
+        wf = enc.conv2.weight.detach()
+        return ops.conv_weight_to_kc(wf if wf.dtype == F32 else wf.float().contiguous())
+    return st.cache.get("conv2.w", [enc.conv2.weight], build)
+
+
 def encoder_forward(st: _State, input_features, save=False):
-    """[B, n_mels, 2*S] fp32 -> LayerNorm'd hidden states as bf16 [B*S, d].  Inference-only schedule (the encoder is
-    frozen on the reference recipe, ref:training/run_distillation.py:1023-1026 / README `--freeze_encoder`)."""
+    """[B, n_mels, 2*S] fp32 -> LayerNorm'd hidden states as bf16 [B*S, d].  save=False is the inference schedule used when
+    the encoder is frozen (the reference recipe, ref:training/run_distillation.py:1023-1026 / README `--freeze_encoder`);
+    save=True keeps what encoder_backward needs (variant A: trainable encoder)."""
     enc = st.m
     cfg = enc.config
     if save:
-        raise NotImplementedError(
-            "training the encoder (variant A) needs the encoder backward schedule, which is not built yet; "
-            "freeze it as the reference recipe does (`--freeze_encoder`)")
+        return encoder_forward_train(st, input_features)
     expected = cfg.max_source_positions * 2
     if input_features.shape[-1] != expected:       # HF:models/whisper/modeling_whisper.py:613-617
         raise ValueError(f"Whisper expects the mel input features to be of length {expected}, but found "
@@ -189,46 +208,159 @@ def encoder_forward(st: _State, input_features, save=False):
     c = st.cache
     mel = input_features.to(F32).contiguous()
     a1 = ops.im2col_conv1(mel)                                          # [B*L, ld1]
-
-    def build_w1(old):
-        w = torch.zeros((d, a1.shape[1]), dtype=BF16, device=mel.device) if old is None else old
-        _to_bf16(w[:, :3 * C], enc.conv1.weight)
-        return w
-    w1 = c.get("conv1.w", [enc.conv1.weight], build_w1)
+    w1 = _conv1_w(st, a1.shape[1])
     x1 = ops.gemm(a1, w1, bias=f32_of(c, "conv1.b", enc.conv1.bias), act=1)            # gelu(conv1) [B*L, d]
     del a1
     a2 = ops.im2col_conv2(x1, B, L, d)                                                # [B*S, 3d]
     del x1
-
-    def build_w2(old):
-        wf = enc.conv2.weight.detach()
-        return ops.conv_weight_to_kc(wf if wf.dtype == F32 else wf.float().contiguous())
-    w2 = c.get("conv2.w", [enc.conv2.weight], build_w2)
+    w2 = _conv2_w(st)
     y = ops.gemm(a2, w2, bias=f32_of(c, "conv2.b", enc.conv2.bias), act=1)             # gelu(conv2) [B*S, d]
     del a2
     M = B * S
-    x = f32_of(c, "pos", enc.embed_positions.weight)[:S]                               # + positions, fused below
-    x_mod = S
-    x_buf = torch.empty((M, d), dtype=F32, device=mel.device)
+    # Residual stream x (fp32, [M, d]) lives in one buffer.  Layer 0's LayerNorm kernel forms x = positions + gelu(conv2);
+    # after that every sub-layer output is ADDED INTO x by its GEMM epilogue (TMA reduce-add of the fp32 accumulator + bias),
+    # so the LayerNorm kernels only read x and write the bf16 normalised rows -- half the HBM traffic of add+LN, and the
+    # sub-layer output is never rounded to bf16 before the residual add.
+    pos = f32_of(c, "pos", enc.embed_positions.weight)[:S]
+    x = torch.empty((M, d), dtype=F32, device=mel.device)
     for i, layer in enumerate(enc.layers):
         k = f"l{i}"
         w = _attn_weights(st, k + ".sa", layer.self_attn, fuse_qkv=True)
         g, b_ = _ln(st, k + ".ln1", layer.self_attn_layer_norm)
-        _, h, _, _ = ops.add_layernorm(x, y, g, b_, rows=M, d=d, x_rows_mod=x_mod, x_out=x_buf)
-        x, x_mod = x_buf, 0
+        if i == 0:
+            _, h, _, _ = ops.add_layernorm(pos, y, g, b_, rows=M, d=d, x_rows_mod=S, x_out=x)
+            del y
+        else:
+            _, h, _, _ = ops.add_layernorm(x, None, g, b_, rows=M, d=d, write_x=False)
         qkv = ops.gemm(h, w["wqkv"], bias=w["bqkv"])
         o, _ = ops.attention_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], B, H, S, S, causal=False, out=h,
                                  need_lse=False, use_tc=USE_TC_ATTENTION)
         del qkv
-        y = ops.gemm(o, w["wo"], bias=w["bo"], out=y)
+        ops.gemm(o, w["wo"], bias=w["bo"], out=x, accumulate=True)                       # x += out_proj(attn)
         g, b_ = _ln(st, k + ".ln2", layer.final_layer_norm)
-        _, h, _, _ = ops.add_layernorm(x, y, g, b_, rows=M, d=d, x_out=x_buf)
+        _, h, _, _ = ops.add_layernorm(x, None, g, b_, rows=M, d=d, write_x=False)
         a = ops.gemm(h, bf16_of(c, k + ".fc1.w", layer.fc1.weight), bias=f32_of(c, k + ".fc1.b", layer.fc1.bias), act=1)
-        y = ops.gemm(a, bf16_of(c, k + ".fc2.w", layer.fc2.weight), bias=f32_of(c, k + ".fc2.b", layer.fc2.bias), out=y)
+        ops.gemm(a, bf16_of(c, k + ".fc2.w", layer.fc2.weight), bias=f32_of(c, k + ".fc2.b", layer.fc2.bias), out=x,
+                 accumulate=True)                                                          # x += fc2(gelu(fc1))
         del a
     g, b_ = _ln(st, "ln_f", enc.layer_norm)
-    _, out, _, _ = ops.add_layernorm(x, y, g, b_, rows=M, d=d, x_rows_mod=x_mod, write_x=False)
+    if len(enc.layers) == 0:
+        _, out, _, _ = ops.add_layernorm(pos, y, g, b_, rows=M, d=d, x_rows_mod=S, write_x=False)
+    else:
+        _, out, _, _ = ops.add_layernorm(x, None, g, b_, rows=M, d=d, write_x=False)
     return out, None
+
+
+def encoder_forward_train(st: _State, input_features):
+    """Training schedule of the encoder: same arithmetic as encoder_forward, but pre-activations, LayerNorm inputs /
+    statistics, fused QKV, attention outputs and log-sum-exps are kept for encoder_backward."""
+    enc = st.m
+    cfg = enc.config
+    expected = cfg.max_source_positions * 2
+    if input_features.shape[-1] != expected:
+        raise ValueError(f"Whisper expects the mel input features to be of length {expected}, but found "
+                         f"{input_features.shape[-1]}. Make sure to pad the input mel features to {expected}.")
+    B, C, L = input_features.shape
+    d, S, H = cfg.d_model, cfg.max_source_positions, cfg.encoder_attention_heads
+    c = st.cache
+    M = B * S
+    mel = input_features.to(F32).contiguous()
+    a1 = ops.im2col_conv1(mel)
+    w1 = _conv1_w(st, a1.shape[1])
+    pre1 = ops.gemm(a1, w1, bias=f32_of(c, "conv1.b", enc.conv1.bias))                   # conv1 pre-activation [B*L, d]
+    x1 = ops.gelu_fwd(pre1)
+    a2 = ops.im2col_conv2(x1, B, L, d)
+    del x1
+    w2 = _conv2_w(st)
+    pre2 = ops.gemm(a2, w2, bias=f32_of(c, "conv2.b", enc.conv2.bias))                   # conv2 pre-activation [M, d]
+    y = ops.gelu_fwd(pre2)
+    ctx = {"B": B, "C": C, "L": L, "a1": a1, "pre1": pre1, "a2": a2, "pre2": pre2, "layers": []}
+    x = f32_of(c, "pos", enc.embed_positions.weight)[:S]
+    x_mod = S
+    for i, layer in enumerate(enc.layers):
+        k = f"l{i}"
+        w = _attn_weights(st, k + ".sa", layer.self_attn, fuse_qkv=True)
+        g, b_ = _ln(st, k + ".ln1", layer.self_attn_layer_norm)
+        xa, h1, mu1, rs1 = ops.add_layernorm(x, y, g, b_, rows=M, d=d, x_rows_mod=x_mod, save_stats=True)
+        x_mod = 0
+        qkv = ops.gemm(h1, w["wqkv"], bias=w["bqkv"])
+        o, lse = ops.attention_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], B, H, S, S, causal=False, need_lse=True,
+                                   use_tc=USE_TC_ATTENTION)
+        y1 = ops.gemm(o, w["wo"], bias=w["bo"])
+        g, b_ = _ln(st, k + ".ln2", layer.final_layer_norm)
+        xb, h2, mu2, rs2 = ops.add_layernorm(xa, y1, g, b_, rows=M, d=d, save_stats=True)
+        del y1
+        hpre = ops.gemm(h2, bf16_of(c, k + ".fc1.w", layer.fc1.weight), bias=f32_of(c, k + ".fc1.b", layer.fc1.bias))
+        a = ops.gelu_fwd(hpre)
+        y = ops.gemm(a, bf16_of(c, k + ".fc2.w", layer.fc2.weight), bias=f32_of(c, k + ".fc2.b", layer.fc2.bias))
+        ctx["layers"].append(dict(xa=xa, h1=h1, mu1=mu1, rs1=rs1, qkv=qkv, o=o, lse=lse, xb=xb, h2=h2, mu2=mu2, rs2=rs2,
+                                  hpre=hpre, a=a))
+        x = xb
+    g, b_ = _ln(st, "ln_f", enc.layer_norm)
+    xf, out, muf, rsf = ops.add_layernorm(x, y, g, b_, rows=M, d=d, x_rows_mod=x_mod, save_stats=True)
+    ctx.update(xf=xf, muf=muf, rsf=rsf)
+    return out, ctx
+
+
+def encoder_backward(st: _State, ctx, denc_bf16):
+    """denc_bf16: bf16 [B*S, d] gradient wrt the encoder's LayerNorm'd output.  Accumulates every trainable encoder
+    parameter gradient into .grad (autograd of HF:models/whisper/modeling_whisper.py:593-647)."""
+    enc = st.m
+    cfg = enc.config
+    d, S, H = cfg.d_model, cfg.max_source_positions, cfg.encoder_attention_heads
+    B, C, L = ctx["B"], ctx["C"], ctx["L"]
+    M = B * S
+    c = st.cache
+    g, _ = _ln(st, "ln_f", enc.layer_norm)
+    dx, dxb = _ln_bwd(denc_bf16, ctx["xf"], ctx["muf"], ctx["rsf"], enc.layer_norm, g, None, M, d)
+    for i in reversed(range(len(enc.layers))):
+        layer, Lc, k = enc.layers[i], ctx["layers"][i], f"l{i}"
+        da = _linear_bwd(dxb, Lc["a"], bf16_of(c, k + ".fc2.w", layer.fc2.weight), layer.fc2.weight, layer.fc2.bias)
+        dhpre = ops.gelu_bwd(da, Lc["hpre"])
+        del da
+        dh2 = _linear_bwd(dhpre, Lc["h2"], bf16_of(c, k + ".fc1.w", layer.fc1.weight), layer.fc1.weight, layer.fc1.bias)
+        del dhpre
+        g, _ = _ln(st, k + ".ln2", layer.final_layer_norm)
+        dx, dxb = _ln_bwd(dh2, Lc["xb"], Lc["mu2"], Lc["rs2"], layer.final_layer_norm, g, dx, M, d)
+        sa = layer.self_attn
+        ws = _attn_weights(st, k + ".sa", sa, fuse_qkv=True)
+        do = _linear_bwd(dxb, Lc["o"], ws["wo"], sa.out_proj.weight, sa.out_proj.bias)
+        qkv = Lc["qkv"]
+        dqkv = torch.empty((M, 3 * d), dtype=BF16, device=qkv.device)
+        ops.attention_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], Lc["o"], do, Lc["lse"], B, H, S, S, False,
+                          dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:])
+        _linear_bwd(dqkv[:, :d], Lc["h1"], None, sa.q_proj.weight, sa.q_proj.bias, need_dx=False)
+        _linear_bwd(dqkv[:, d:2 * d], Lc["h1"], None, sa.k_proj.weight, None, need_dx=False)
+        _linear_bwd(dqkv[:, 2 * d:], Lc["h1"], None, sa.v_proj.weight, sa.v_proj.bias, need_dx=False)
+        dh1 = ops.gemm(dqkv, ws["wqkv"], b_mn=True)
+        del dqkv
+        g, _ = _ln(st, k + ".ln1", layer.self_attn_layer_norm)
+        dx, dxb = _ln_bwd(dh1, Lc["xa"], Lc["mu1"], Lc["rs1"], layer.self_attn_layer_norm, g, dx, M, d)
+        ctx["layers"][i] = None                       # release this layer's activations
+    # conv stem.  dxb = d loss / d gelu(conv2) (the position table is frozen)
+    d2 = ops.gelu_bwd(dxb, ctx["pre2"])                                                   # [M, d] wrt conv2 pre-activation
+    w2p = enc.conv2.weight
+    if w2p.requires_grad:
+        gkc = ops.gemm(d2, ctx["a2"], a_mn=True, b_mn=True, out_dtype=F32)                # [d, 3d] in (k, c) column order
+        _abi_call_conv_wgrad(gkc, _grad_buf(w2p), d, d)
+    if enc.conv2.bias.requires_grad:
+        ops.colsum(d2, out=_grad_buf(enc.conv2.bias), accumulate=True)
+    w2 = _conv2_w(st)
+    da2 = ops.gemm(d2, w2, b_mn=True)                                                      # [M, 3d]
+    d1 = ops.col2im_conv2_gelu_bwd(da2, ctx["pre1"], B, L, d)                              # [B*L, d] wrt conv1 pre-activation
+    del da2
+    w1p = enc.conv1.weight
+    if w1p.requires_grad:
+        ops.gemm(d1, ctx["a1"][:, :3 * C], a_mn=True, b_mn=True, out=_grad_buf(w1p).reshape(d, 3 * C), accumulate=True)
+    if enc.conv1.bias.requires_grad:
+        ops.colsum(d1, out=_grad_buf(enc.conv1.bias), accumulate=True)
+
+
+def _abi_call_conv_wgrad(gkc, dw, O, Cc):
+    from . import _abi
+    import ctypes as C
+    _abi.call("dwb_conv_wgrad_kc_to_ck", C.c_void_p(gkc.data_ptr()), C.c_void_p(dw.data_ptr()), O, Cc, 1,
+              C.c_void_p(torch.cuda.current_stream().cuda_stream))
 
 
 # =================================================================================================================
@@ -396,8 +528,13 @@ def _check_trainable_dtypes(model):
                             "(ref:training/run_distillation.py:995-1004 loads it in fp32)")
 
 
-def run_encoder(model, input_features, enc_in):
-    """Returns bf16 [B*S, d] encoder states from features or from caller-provided hidden states."""
+def encoder_is_trainable(model) -> bool:
+    return any(p.requires_grad for n, p in model.model.encoder.named_parameters() if "embed_positions" not in n)
+
+
+def run_encoder(model, input_features, enc_in, save=False):
+    """Returns (bf16 [B*S, d] encoder states, S, ctx) from features or from caller-provided hidden states.
+    save=True (trainable encoder, variant A) keeps the activations encoder_backward needs in ctx."""
     cfg = model.config
     if enc_in is not None:
         e = enc_in.reshape(-1, cfg.d_model)
@@ -405,15 +542,18 @@ def run_encoder(model, input_features, enc_in):
             e = ops.cast_f32_to_bf16(e.contiguous())
         elif e.dtype != BF16:
             raise TypeError(f"encoder_outputs dtype {e.dtype} unsupported")
-        return e.contiguous(), e.shape[0] // enc_in.shape[0]
+        return e.contiguous(), e.shape[0] // enc_in.shape[0], None
     if input_features is None:
         raise ValueError("input_features or encoder_outputs are required")
-    encoder = model.model.encoder
-    if any(p.requires_grad for n, p in encoder.named_parameters() if "embed_positions" not in n) and torch.is_grad_enabled():
-        raise NotImplementedError(
-            "the encoder has trainable parameters: only the frozen-encoder recipe (ref `--freeze_encoder`) is built so far")
-    out, _ = encoder_forward(state_of(encoder), input_features, save=False)
-    return out, cfg.max_source_positions
+    out, ectx = encoder_forward(state_of(model.model.encoder), input_features, save=save)
+    return out, cfg.max_source_positions, ectx
+
+
+def backward_through_model(model, dctx, ectx, dlogits_bf16):
+    """Decoder (+ encoder when ectx is given) backward from the bf16 logits gradient; gradients land in .grad."""
+    denc = decoder_backward(state_of(model.model.decoder), dctx, dlogits_bf16, want_denc=ectx is not None)
+    if ectx is not None:
+        encoder_backward(state_of(model.model.encoder), ectx, ops.cast_f32_to_bf16(denc))
 
 
 class ModelForwardFn(torch.autograd.Function):
@@ -422,8 +562,8 @@ class ModelForwardFn(torch.autograd.Function):
 
     @staticmethod
     def run(model, input_features, decoder_input_ids, enc_in):
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in model.model.decoder.parameters())
-        anchor = next((p for p in model.model.decoder.parameters() if p.requires_grad), None) if need_grad else None
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters())
+        anchor = next((p for p in model.parameters() if p.requires_grad), None) if need_grad else None
         if need_grad:
             _check_trainable_dtypes(model)
             return ModelForwardFn.apply(model, input_features, decoder_input_ids, enc_in, anchor)
@@ -433,15 +573,15 @@ class ModelForwardFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, input_features, decoder_input_ids, enc_in, anchor):
         cfg = model.config
-        enc, S = run_encoder(model, input_features, enc_in)
+        save = ctx is not None
+        enc, S, ectx = run_encoder(model, input_features, enc_in, save=save and enc_in is None and encoder_is_trainable(model))
         B, T = decoder_input_ids.shape
         dst = state_of(model.model.decoder)
-        save = ctx is not None
         hf, dctx = decoder_forward(dst, decoder_input_ids, enc, B, S, save)
         buf = lm_head(dst, hf)
         logits = buf.view(B, T, -1)[:, :, :cfg.vocab_size]
         if save:
-            ctx.model, ctx.dctx = model, dctx
+            ctx.model, ctx.dctx, ctx.ectx = model, dctx, ectx
             ctx.mark_non_differentiable(enc)
         return logits, enc
 
@@ -461,8 +601,8 @@ class ModelForwardFn(torch.autograd.Function):
             ops.cast_f32_to_bf16(pad, dl[:, :pad.shape[1]])
         else:
             ops.cast_f32_to_bf16(src, dl[:, :V])
-        decoder_backward(state_of(model.model.decoder), ctx.dctx, dl)
-        ctx.dctx = None
+        backward_through_model(model, ctx.dctx, ctx.ectx, dl)
+        ctx.dctx = ctx.ectx = None
         return None, None, None, None, None
 
 

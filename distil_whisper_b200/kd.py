@@ -27,7 +27,7 @@ class _KDStepFn(torch.autograd.Function):
             raise ValueError("student and teacher vocabularies differ")
         train = ctx is not None
         # ---- student (ref :1472)
-        enc_s, S = engine.run_encoder(student, feats, None)
+        enc_s, S, ectx = engine.run_encoder(student, feats, None, save=train and engine.encoder_is_trainable(student))
         sst = engine.state_of(student.model.decoder)
         hf_s, dctx = engine.decoder_forward(sst, dec_in, enc_s, B, S, save=train)
         logits_s = engine.lm_head(sst, hf_s)
@@ -40,14 +40,14 @@ class _KDStepFn(torch.autograd.Function):
             enc_t = enc_s
         else:
             t_in = dec_in
-            enc_t, _ = engine.run_encoder(teacher, feats, None)
+            enc_t, _, _ = engine.run_encoder(teacher, feats, None)
         hf_t, _ = engine.decoder_forward(tst, t_in, enc_t, B, S, save=False)
         logits_t = engine.lm_head(tst, hf_t)
         # ---- fused loss head (ref :1484-1493)
         metrics, dl = ops.kd_loss(logits_s, logits_t, labels, V, temperature, 0.8 * loss_scale, step.kl_weight * loss_scale,
                                   want_grad=train)
         if train:
-            ctx.step, ctx.dctx, ctx.dl = step, dctx, dl
+            ctx.step, ctx.dctx, ctx.ectx, ctx.dl = step, dctx, ectx, dl
         step.last_student_logits = logits_s.view(B, T, -1)[:, :, :V] if step.keep_logits else None
         step.last_teacher_logits = logits_t.view(B, T, -1)[:, :, :V] if step.keep_logits else None
         step.last_encoder_states = enc_s
@@ -57,8 +57,8 @@ class _KDStepFn(torch.autograd.Function):
     def backward(ctx, g_loss, _g_metrics):
         # d loss / d logits was produced by the loss kernel with loss_scale folded in; `loss.backward()` supplies 1.
         step = ctx.step
-        engine.decoder_backward(engine.state_of(step.student.model.decoder), ctx.dctx, ctx.dl)
-        ctx.dctx = ctx.dl = None
+        engine.backward_through_model(step.student, ctx.dctx, ctx.ectx, ctx.dl)
+        ctx.dctx = ctx.ectx = ctx.dl = None
         return None, None, None, None, None
 
 
@@ -82,7 +82,7 @@ class DistillationStep:
         self.last_student_logits = self.last_teacher_logits = self.last_encoder_states = None
 
     def _anchor(self):
-        return next((p for p in self.student.model.decoder.parameters() if p.requires_grad), None)
+        return next((p for p in self.student.parameters() if p.requires_grad), None)
 
     def train_step(self, batch, temperature: float = 2.0, loss_scale: float = 1.0):
         """loss_scale: fold 1/gradient_accumulation_steps here (the gradient is produced inside the loss kernel)."""
@@ -90,10 +90,8 @@ class DistillationStep:
         self.teacher.eval()
         anchor = self._anchor()
         if anchor is None:
-            raise RuntimeError("student has no trainable decoder parameters")
+            raise RuntimeError("student has no trainable parameters")
         engine._check_trainable_dtypes(self.student)
-        if any(p.requires_grad for n, p in self.student.model.encoder.named_parameters() if "embed_positions" not in n):
-            raise NotImplementedError("trainable student encoder (variant A) is not built yet; use the --freeze_encoder recipe")
         loss, m = _KDStepFn.apply(self, batch, float(temperature), float(loss_scale), anchor)
         return loss, {"loss": loss, "ce_loss": m[1], "kl_loss": m[2]}
 
@@ -104,11 +102,9 @@ class DistillationStep:
         self.student.train()
         self.teacher.eval()
         engine._check_trainable_dtypes(self.student)
-        if any(p.requires_grad for n, p in self.student.model.encoder.named_parameters() if "embed_positions" not in n):
-            raise NotImplementedError("trainable student encoder (variant A) is not built yet; use the --freeze_encoder recipe")
         ctx = _PlainCtx()
         loss, m = _KDStepFn.forward(ctx, self, batch, float(temperature), float(loss_scale), None)
-        engine.decoder_backward(engine.state_of(self.student.model.decoder), ctx.dctx, ctx.dl)
+        engine.backward_through_model(self.student, ctx.dctx, ctx.ectx, ctx.dl)
         return loss, {"loss": loss, "ce_loss": m[1], "kl_loss": m[2]}
 
     @torch.no_grad()

@@ -160,6 +160,12 @@ def im2col_conv2(x, B, L, d):
     return out
 
 
+def col2im_conv2_gelu_bwd(g, pre1, B, L, d):
+    out = torch.empty((B * L, d), dtype=BF16, device=g.device)
+    _abi.call("dwb_col2im_conv2_gelu_bwd", _ptr(g), _ptr(pre1), _ptr(out), B, L, d, _stream())
+    return out
+
+
 def embed_fwd(ids, E, P, B, T, d, vocab):
     assert ids.dtype == torch.int64 and ids.is_contiguous() and E.dtype == P.dtype
     x = torch.empty((B * T, d), dtype=F32, device=ids.device)

@@ -79,6 +79,8 @@ int dwb_conv_wgrad_kc_to_ck(const float* g, float* dw, int O, int C, int accumul
  * :620 (conv2 on channels-last x [B,L,d] bf16 -> [B*L/2, 3d], col k*d+c). */
 int dwb_im2col_conv1(const float* mel, void* out_bf16, int B, int C, int L, int ld, void* stream);
 int dwb_im2col_conv2(const void* x_bf16, void* out_bf16, int B, int L, int d, void* stream);
+/* Backward of :620/:619: col2im of the conv2 input gradient g [B*L/2, 3d] onto [B, L, d], times gelu'(conv1 pre-activation). */
+int dwb_col2im_conv2_gelu_bwd(const void* g_bf16, const void* pre1_bf16, void* out_bf16, int B, int L, int d, void* stream);
 
 /* ---- decoder embeddings: HF:models/whisper/modeling_whisper.py:738 (embed_tokens, padding_idx) + :755 (positions) */
 int dwb_embed_fwd(const int64_t* ids, const void* E, const void* P, int table_is_f32, float* x, int B, int T, int d, int vocab,

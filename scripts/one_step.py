@@ -11,7 +11,7 @@ from distil_whisper_b200.optim import FusedAdamW  # noqa: E402
 
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
-student, teacher = bench.build_models(dev)
+student, teacher = bench.build_models(dev, os.environ.get("DWB_VARIANT", "B"))
 step = DistillationStep(student, teacher, kl_weight=1.0)
 opt = FusedAdamW.for_model(student, lr=1e-4, max_grad_norm=1.0)
 batch = {k: v.to(dev) for k, v in bench.synthetic_batch(bench.BATCH, bench.N_TOK, 1234, bench.STUDENT).items()}

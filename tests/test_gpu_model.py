@@ -96,6 +96,39 @@ def test_tiny_kd_step_matches_hf_golden(golden_dir):
     assert float(student.model.decoder.embed_tokens.weight.grad[sc.pad_token_id].abs().sum()) > 0
 
 
+def test_tiny_kd_step_variant_a_trainable_encoder_matches_hf_golden(golden_dir):
+    """Branch A: trainable student encoder + the teacher's own encoder (teacher_model(**batch), ref :1481)."""
+    from distil_whisper_b200.kd import DistillationStep
+    g = np.load(os.path.join(golden_dir, "kd_tiny.npz"))
+    s_seed, t_seed, b_seed = [int(x) for x in g["seeds"]]
+    sc, tc = wo.PRESETS["tiny-student"], wo.PRESETS["tiny-teacher"]
+    student = _build(sc, wo.init_state_dict(sc, s_seed))
+    teacher = _build(tc, wo.init_state_dict(tc, t_seed), dtype=torch.bfloat16)
+    step = DistillationStep(student, teacher, kl_weight=1.0, keep_logits=True)
+    assert not step.share_hidden_states and teacher.model.encoder is not student.model.encoder
+    batch = _cuda(wo.synthetic_batch(sc, batch=3, n_tok=12, seed=b_seed))
+    loss, metrics = step.train_step(batch, temperature=2.0)
+    loss.backward()
+    assert abs(loss.item() - float(g["A_loss"])) / float(g["A_loss"]) < LOSS_REL
+    assert abs(metrics["kl_loss"].item() - float(g["A_kl_loss"])) / float(g["A_kl_loss"]) < 5e-2
+    assert _rel(step.last_student_logits, g["A_student_logits"]) < LOGITS_REL
+    assert _rel(step.last_teacher_logits, g["A_teacher_logits"]) < 2 * LOGITS_REL
+    names = [str(n) for n in g["A_grad_names"]]
+    params = dict(student.named_parameters())
+    got = {n for n, p in params.items() if p.grad is not None and p.requires_grad}
+    assert got == set(names), sorted(got ^ set(names))
+    bad = []
+    for n, norm in zip(names, g["A_grad_norms"]):
+        gr = params[n].grad
+        tol = 2 * GRAD_REL if (".q_proj." in n or ".k_proj." in n) else GRAD_REL
+        if abs(float(gr.norm()) - norm) / (norm + 1e-12) > tol:
+            bad.append((n, "norm", float(gr.norm()), norm))
+        key = f"A_grad::{n}"
+        if key in g.files and _rel(gr, g[key]) > tol:
+            bad.append((n, "rel", _rel(gr, g[key])))
+    assert not bad, bad
+
+
 def test_generic_forward_backward_path_matches_oracle():
     """model(**batch).loss.backward() -- the un-fused HF-shaped path (CE only) -- against the fp32 oracle."""
     sc = wo.PRESETS["tiny-student"]
@@ -200,7 +233,7 @@ def test_cuda_graph_replay_matches_eager():
         le, _ = step_e.train_step(batch, 2.0)
         le.backward()
         lg, _ = graphed(batch)
-        assert abs(le.item() - lg.item()) < 1e-6 * abs(le.item()) + 1e-7
+        assert abs(le.item() - lg.item()) < 2e-5 * abs(le.item())      # weights drift apart by atomics-order round-off
         assert _rel(opt_g.flat.grad, opt_e.flat.grad) < 2e-4          # fp32 atomics order only (dQ, LN/bias column sums)
         opt_e.step()
         opt_g.step()
