@@ -232,6 +232,8 @@ def main():
     final_loss = float(one_step(dev_batch).item())
 
     if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
         return
     peak, peak_src = peaks()
     utt = BATCH * world
@@ -275,6 +277,8 @@ def main():
             out["cpu_baseline"] = {"value": None, "unit": "utterances/s", "cores": os.cpu_count(), "kind": "reference",
                                    "sample": f"failed: {type(ex).__name__}: {ex}"}
     print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -2,7 +2,7 @@
 //   per CTA: one (batch, head, 128-query tile); loops over 128-key tiles
 //   S = Q K^T      tcgen05.mma 128x128x64  (Q, K tiles: TMA, 128B swizzle, K-major)        -> TMEM cols [0,128)
 //   softmax        one thread per query row (tcgen05.ld 32x32b: lane == row, no shuffles), online max/sum in fp32,
-//                  P (bf16) written to a swizzled smem tile
+//                  P (bf16 pairs) written back to TMEM (tcgen05.st) and consumed from there as the A operand of P V
 //   O += P V       tcgen05.mma 128x64x128  (V tile is the MN-major B operand: no transpose)  -> TMEM cols [128,192),
 //                  accumulated in TMEM across key tiles; rescaled (tcgen05.ld/st) only when a row maximum grows by > 2^8
 //                  ("lazy rescale"), normalised by the row sum at the end, TMA store
@@ -18,8 +18,9 @@ namespace dwb {
 constexpr int TA_BQ = 128, TA_BK = 128, TA_HD = 64;
 constexpr int TA_THREADS = 256;   // warps 0-3 softmax warpgroup; warp 4 TMA, warp 5 MMA, warps 6-7 idle (complete the 2nd warpgroup)
 constexpr int TA_TILE_BYTES = 128 * 128;            // 128 rows x 128 B
-constexpr int TA_TILES_BYTES = TA_TILE_BYTES /*Q*/ + 2 * 2 * TA_TILE_BYTES /*K,V x 2 stages*/ + 2 * TA_TILE_BYTES /*P*/;
-constexpr int TA_BAR_BYTES = 96;
+constexpr int TA_KV_STAGES = 3;
+constexpr int TA_TILES_BYTES = TA_TILE_BYTES /*Q, reused for the output tile*/ + TA_KV_STAGES * 2 * TA_TILE_BYTES /*K,V*/;
+constexpr int TA_BAR_BYTES = 112;
 // two CTAs per SM: 2 * (dyn + 1 KB system reserve) <= 228 KB  ->  dyn <= 115712; the slack absorbs the 1 KB round-up
 constexpr int TA_SMEM = 115712;
 static_assert(TA_TILES_BYTES + TA_BAR_BYTES + 896 <= TA_SMEM, "smem budget");
@@ -50,18 +51,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   }
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + TA_TILE_BYTES;                  // stage s: K at s*32K, V at s*32K + 16K
-  uint8_t* sP = sKV + 4 * TA_TILE_BYTES;              // two 128x64 halves
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * TA_TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + TA_KV_STAGES * 2 * TA_TILE_BYTES);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;      // [2]
-  uint64_t* kv_empty = bars + 3;     // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* s_empty = bars + 6;
-  uint64_t* p_full = bars + 7;
-  uint64_t* p_empty = bars + 8;
-  uint64_t* o_full = bars + 9;
-  uint64_t* o_empty = bars + 10;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* kv_full = bars + 1;      // [3]
+  uint64_t* kv_empty = bars + 4;     // [3]
+  uint64_t* s_full = bars + 7;
+  uint64_t* s_empty = bars + 8;
+  uint64_t* p_full = bars + 9;
+  uint64_t* p_empty = bars + 10;
+  uint64_t* o_full = bars + 11;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * TA_BQ;
@@ -71,11 +70,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_o);
     mbar_init(q_full, 1);
-    mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
-    mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
+    for (int i = 0; i < TA_KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(s_full, 1); mbar_init(s_empty, 128);
     mbar_init(p_full, 128); mbar_init(p_empty, 1);
-    mbar_init(o_full, 1); mbar_init(o_empty, 128);   // o_empty unused since O accumulates in TMEM
+    mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 5) {
@@ -86,8 +84,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_s = tmem_base;            // 128 columns of scores
-  const uint32_t tmem_o = tmem_base + 128;      // 64 columns: P V of the current tile
+  const uint32_t tmem_s = tmem_base;            // 128 columns: fp32 scores of the current key tile
+  const uint32_t tmem_p = tmem_base + 128;      //  64 columns: bf16 probabilities, 2 keys per 32-bit column (A operand of P V)
+  const uint32_t tmem_o = tmem_base + 192;      //  64 columns: fp32 output accumulator
 
   // register re-distribution between the two warpgroups (launch: 128/thread for 2 CTAs/SM): 208 for softmax, 48 for the rest
   if (warp >= 4) {
@@ -99,8 +98,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       mbar_expect_tx(q_full, TA_TILE_BYTES);
       tma_load_3d(&tmap_q, q_full, sQ, h * TA_HD, q0, b);
       for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        const int st = j % TA_KV_STAGES;
+        mbar_wait(&kv_empty[st], ((j / TA_KV_STAGES) & 1) ^ 1);
         mbar_expect_tx(&kv_full[st], 2 * TA_TILE_BYTES);
         tma_load_3d(&tmap_k, &kv_full[st], sKV + st * 2 * TA_TILE_BYTES, h * TA_HD, j * TA_BK, b);
         tma_load_3d(&tmap_v, &kv_full[st], sKV + st * 2 * TA_TILE_BYTES + TA_TILE_BYTES, h * TA_HD, j * TA_BK, b);
@@ -115,10 +114,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
       mbar_wait(q_full, 0);
       const uint64_t dq = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-      const uint64_t dp0 = umma_desc_sw128(smem_u32(sP), 16, 1024);
       auto issue_qk = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        const int st = j % TA_KV_STAGES;
+        mbar_wait(&kv_full[st], (j / TA_KV_STAGES) & 1);
         mbar_wait(s_empty, (j & 1) ^ 1);
         tc_fence_after();
         const uint64_t dk = umma_desc_sw128(smem_u32(sKV + st * 2 * TA_TILE_BYTES), 16, 1024);
@@ -128,16 +126,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       };
       issue_qk(0);
       for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
+        const int st = j % TA_KV_STAGES;
         if (j + 1 < n_kv) issue_qk(j + 1);
-        mbar_wait(p_full, j & 1);                  // P_j written (and any rescale of O finished)
+        mbar_wait(p_full, j & 1);                  // P_j is in TMEM (and any rescale of O finished)
         tc_fence_after();
         const uint64_t dv = umma_desc_sw128(smem_u32(sKV + st * 2 * TA_TILE_BYTES + TA_TILE_BYTES), TA_TILE_BYTES, 1024);
 #pragma unroll
-        for (int k = 0; k < TA_BK / 16; ++k) {
-          const uint64_t dp = dp0 + (uint64_t)((k >> 2) * (TA_TILE_BYTES >> 4) + 2 * (k & 3));
-          tc_mma_ss(tmem_o, dp, dv + (uint64_t)(k * 128), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);   // O accumulates in TMEM
-        }
+        for (int k = 0; k < TA_BK / 16; ++k)       // A = P from TMEM: 16 keys = 8 columns per step; O accumulates in TMEM
+          tc_mma_ts(tmem_o, tmem_p + 8 * k, dv + (uint64_t)(k * 128), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
         tc_commit(o_full);
         tc_commit(&kv_empty[st]);
         tc_commit(p_empty);
@@ -152,7 +148,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const int row = warp * 32 + lane;                       // query row of this thread == TMEM lane
     const uint32_t t_s = tmem_s + ((uint32_t)(warp * 32) << 16);
     const uint32_t t_o = tmem_o + ((uint32_t)(warp * 32) << 16);
-    const uint32_t sP_row = smem_u32(sP) + row * 128;
+    const uint32_t t_p = tmem_p + ((uint32_t)(warp * 32) << 16);
     const int sw = row & 7;
     float m_ref = -INFINITY, l_run = 0.f;
 
@@ -206,27 +202,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         m_ref = mx;
       }
       const float msc = m_ref * p.scale_log2;
-      mbar_wait(p_empty, (j & 1) ^ 1);                      // P V of the previous tile has consumed sP
+      mbar_wait(p_empty, (j & 1) ^ 1);                      // P V of the previous tile has consumed P
+      tc_fence_after();
       float ls[4] = {0.f, 0.f, 0.f, 0.f};          // independent partial sums (no 128-long dependent FADD chain)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
+      for (int c = 0; c < 2; ++c) {                // 64 keys -> 32 packed columns per tcgen05.st
+        uint32_t pk[32];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float e0 = fast_exp2(fmaf(__uint_as_float(v[c * 32 + i]), p.scale_log2, -msc));
-          const float e1 = fast_exp2(fmaf(__uint_as_float(v[c * 32 + i + 1]), p.scale_log2, -msc));
+        for (int i = 0; i < 64; i += 2) {
+          const float e0 = fast_exp2(fmaf(__uint_as_float(v[c * 64 + i]), p.scale_log2, -msc));
+          const float e1 = fast_exp2(fmaf(__uint_as_float(v[c * 64 + i + 1]), p.scale_log2, -msc));
           ls[(i >> 1) & 3] += e0 + e1;
           pk[i >> 1] = pack_bf16x2(e0, e1);
         }
-        const uint32_t half = sP_row + (c >> 1) * TA_TILE_BYTES;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int chunk = (c & 1) * 4 + q4;               // 16 B chunk (8 keys) inside the 128 B half-row
-          st_shared_v4(half + ((chunk ^ sw) << 4), pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
-        }
+        tmem_st_32x32(t_p + c * 32, pk);
       }
+      tmem_st_wait();
       l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-      fence_proxy_async_smem();
+      tc_fence_before();
       mbar_arrive(p_full);
     }
     // epilogue: O / l  ->  bf16 tile through sQ (Q is dead: every QK^T has completed) -> TMA store clips rows >= Sq
