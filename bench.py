@@ -120,6 +120,21 @@ def run_reference(args):
         "gpu_launches": 0, "loss": loss}))
 
 
+def run_hf_gpu(args):
+    """Context: the reference's own GPU configuration (HF modules, bf16 autocast, sdpa, torch AdamW) on the same box."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle.reference_step import ReferenceKDStep
+    from oracle.whisper_oracle import WhisperDims
+    ref = ReferenceKDStep(WhisperDims(**STUDENT), WhisperDims(**TEACHER), freeze_encoder=args.variant == "B", device="cuda")
+    batch = {k: v.cuda() for k, v in synthetic_batch(BATCH, N_TOK, 1234, STUDENT).items()}
+    sec, loss = ref.time_steps(batch, args.steps, max(args.warmup, 2))
+    print(json.dumps({"impl": "hf_gpu", "metric": "kd_step_utterances_per_s", "value": BATCH / sec, "unit": "utterances/s",
+                      "ms_per_step": sec * 1e3, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "dtype": "bf16 autocast",
+                      "config": {"workload": f"HF transformers Whisper + torch AdamW on the GPU, variant {args.variant}, {BATCH}x(80x3000, {N_TOK} tok)",
+                                 "kind": ref.kind}, "loss": loss}))
+
+
 def build_models(device, variant="B"):
     from distil_whisper_b200.modeling import DistilWhisperB200ForConditionalGeneration
     torch.manual_seed(0)
@@ -138,7 +153,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "hf_gpu"],
+                    help="reference: the reference's CPU path (driver arm).  hf_gpu: HF modules on the GPU (bf16 autocast + sdpa), context only")
     ap.add_argument("--cpu-batch", type=int, default=2, help="utterances per CPU reference step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
@@ -148,6 +164,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "hf_gpu":
+        return run_hf_gpu(args)
     if args.warmup < 3:
         args.warmup = 3
 

@@ -42,7 +42,11 @@ def _hf_model(dims: wo.WhisperDims, dtype=torch.float32):
 class ReferenceKDStep:
     """Frozen + shared encoder recipe (ref README `--freeze_encoder`) or full (variant A) on the CPU."""
 
-    def __init__(self, student_dims, teacher_dims, freeze_encoder=True, threads=None, lr=1e-4, max_grad_norm=1.0, kl_weight=1.0):
+    def __init__(self, student_dims, teacher_dims, freeze_encoder=True, threads=None, lr=1e-4, max_grad_norm=1.0, kl_weight=1.0,
+                 device="cpu"):
+        """device="cuda": the reference's GPU configuration for context (fp32 student under bf16 autocast, bf16 teacher, sdpa,
+        ref:training/run_distillation.py:798-813,985-1004) -- needs transformers."""
+        self.device = torch.device(device)
         if threads:
             torch.set_num_threads(threads)
         self.cores = torch.get_num_threads()
@@ -51,8 +55,8 @@ class ReferenceKDStep:
         self.kl_weight, self.max_grad_norm = kl_weight, max_grad_norm
         self.sc, self.tc = student_dims, teacher_dims
         if self.kind == "reference":
-            self.student = _hf_model(student_dims)
-            self.teacher = _hf_model(teacher_dims)
+            self.student = _hf_model(student_dims).to(self.device)
+            self.teacher = _hf_model(teacher_dims, torch.bfloat16 if self.device.type == "cuda" else torch.float32).to(self.device)
             if freeze_encoder:
                 for p in self.student.model.encoder.parameters():
                     p.requires_grad = False
@@ -76,12 +80,18 @@ class ReferenceKDStep:
             from transformers.modeling_outputs import BaseModelOutput
             self.student.train()
             self.teacher.eval()
-            so = self.student(**batch)
+            cuda = self.device.type == "cuda"
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=cuda):
+                so = self.student(**batch)
             with torch.no_grad():
                 if self.freeze_encoder:
-                    to = self.teacher(encoder_outputs=BaseModelOutput(so.encoder_last_hidden_state), labels=batch["labels"])
+                    enc = so.encoder_last_hidden_state.to(torch.bfloat16) if cuda else so.encoder_last_hidden_state
+                    to = self.teacher(encoder_outputs=BaseModelOutput(enc), labels=batch["labels"])
                 else:
-                    to = self.teacher(**batch)
+                    tb = {k: (v.to(torch.bfloat16) if (cuda and v.is_floating_point()) else v) for k, v in batch.items()}
+                    to = self.teacher(**tb)
+            so.logits = so.logits.float()
+            to.logits = to.logits.float()
             ce = so.loss
             td = nn.functional.softmax(to.logits / temperature, dim=-1)
             sd = nn.functional.log_softmax(so.logits / temperature, dim=-1)
@@ -97,11 +107,16 @@ class ReferenceKDStep:
         return float(loss.detach())
 
     def time_steps(self, batch, steps, warmup):
+        cuda = self.device.type == "cuda"
         for _ in range(warmup):
             self.step(batch)
+        if cuda:
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         last = None
         for _ in range(steps):
             last = self.step(batch)
+        if cuda:
+            torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         return dt / steps, last

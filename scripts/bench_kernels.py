@@ -74,13 +74,42 @@ def bench_attn():
     return out
 
 
+def bench_logmel():
+    """BASELINE.json configs[3]: 1024 x 480000-sample fp32 waveforms -> [1024, 80, 3000]; algorithmic bytes 2.88 MB / utterance."""
+    from distil_whisper_b200.feature_extraction import WhisperFeatureExtractorB200
+    out = []
+    for n_mels, B in ((80, 1024), (128, 1024)):
+        fe = WhisperFeatureExtractorB200(n_mels)
+        wav = torch.randn((B, 480000), device="cuda") * 0.1
+        dst = torch.empty((B, n_mels, 3000), device="cuda")
+        ms = timeit(lambda: fe.extract_device(wav, out=dst), iters=5, warmup=3)
+        byts = B * (480000 * 4 + n_mels * 3000 * 4)
+        # the library path the reference reaches: torch.stft + matmul + log10 (HF _torch_extract_fbank_features on the GPU)
+        win = torch.hann_window(400, device="cuda")
+        filt = torch.from_numpy(fe.mel_filters.astype("float32")).cuda()
+
+        def hf_like():
+            st = torch.stft(wav[:256], 400, 160, window=win, return_complex=True)
+            mag = st[..., :-1].abs() ** 2
+            ls = torch.clamp(filt.T @ mag, min=1e-10).log10()
+            mx = ls.amax(dim=(1, 2), keepdim=True)
+            return (torch.maximum(ls, mx - 8.0) + 4.0) / 4.0
+        ms_t = timeit(hf_like, iters=3, warmup=2) * (B / 256)
+        out.append(dict(n_mels=n_mels, B=B, ms=round(ms, 4), gbps=round(byts / ms / 1e6, 1), utt_per_s=round(B / ms * 1e3),
+                        torch_ms=round(ms_t, 3), torch_gbps=round(byts / ms_t / 1e6, 1)))
+        print(out[-1], flush=True)
+    return out
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["gemm", "attn"]
+    which = sys.argv[1:] or ["gemm", "attn", "logmel"]
     res = {}
     if "gemm" in which:
         res["gemm"] = bench_gemm()
     if "attn" in which:
         res["attn"] = bench_attn()
+    if "logmel" in which:
+        res["logmel"] = bench_logmel()
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/bench_kernels.json", "w") as f:
         json.dump(res, f, indent=1)

@@ -148,6 +148,23 @@ def test_conv_stem_as_gemm(ops, B, C, L, d):
     assert torch.equal(dw, gk.view(d, 3, d).permute(0, 2, 1).contiguous())
 
 
+def test_col2im_conv2_gelu_bwd(ops):
+    """Input gradient of the stride-2 conv (col2im over overlapping windows) fused with conv1's GELU backward."""
+    B, L, d = 2, 20, 64
+    pre1 = _randn((B * L, d), 1, 1.5, torch.bfloat16)
+    g = _randn((B * (L // 2), 3 * d), 2, 1.0, torch.bfloat16)
+    out = ops.col2im_conv2_gelu_bwd(g, pre1, B, L, d)
+    pr = pre1.float().view(B, L, d).requires_grad_(True)
+    x = F.gelu(pr)
+    xp = F.pad(x, (0, 0, 1, 0))                                      # position -1 -> zeros
+    cols = torch.stack([xp[:, k:k + L:2, :][:, :L // 2] for k in range(3)], dim=2)   # [B, L/2, 3, d]: taps 2t-1+k
+    (cols.reshape(B * (L // 2), 3 * d) * g.float()).sum().backward()
+    assert _rel(out, pr.grad.view(B * L, d)) < 6e-3, _rel(out, pr.grad.view(B * L, d))
+    # and the forward im2col agrees with the same tap construction
+    a2 = ops.im2col_conv2(x.detach().bfloat16().reshape(B * L, d).contiguous(), B, L, d)
+    assert torch.equal(a2, cols.detach().bfloat16().reshape(B * (L // 2), 3 * d))
+
+
 # ---------------------------------------------------------------------------------------------- embeddings / small ops
 @pytest.mark.parametrize("table_dtype", [torch.float32, torch.bfloat16])
 def test_embedding_fwd_bwd(ops, table_dtype):
