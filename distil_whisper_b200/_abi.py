@@ -27,6 +27,8 @@ SIGNATURES = {
     "dwb_attention_fwd_tc": (_i, [_p, _l, _p, _l, _p, _l, _p, _l, _p, _i, _i, _i, _i, _i, _i, _f, _p]),
     "dwb_attention_bwd": (_i, [_p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _p, _p, _p, _p, _l, _p, _l,
                                _i, _i, _i, _i, _i, _i, _f, _p]),
+    "dwb_attention_bwd_tc": (_i, [_p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _p, _p, _p, _p, _l, _p, _l,
+                                  _i, _i, _i, _i, _i, _i, _f, _p]),
     "dwb_add_layernorm": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _p]),
     "dwb_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "dwb_cast_f32_to_bf16": (_i, [_p, _l, _p, _l, _i, _i, _f, _p]),
@@ -68,7 +70,7 @@ _lib = None
 
 # kernel launches issued through the ABI (bench.py reads / resets LAUNCHES[0]); entry -> kernels it launches
 LAUNCHES = [0]
-_KERNELS_PER_CALL = {"dwb_attention_bwd": 2, "dwb_kd_loss": 3, "dwb_last_error": 0, "dwb_abi_version": 0, "dwb_check_device": 0,
+_KERNELS_PER_CALL = {"dwb_attention_bwd": 2, "dwb_attention_bwd_tc": 2, "dwb_kd_loss": 3, "dwb_last_error": 0, "dwb_abi_version": 0, "dwb_check_device": 0,
                      "dwb_kd_loss_workspace_bytes": 0, "dwb_logmel_plan_create": 0, "dwb_logmel_plan_destroy": 0}
 
 

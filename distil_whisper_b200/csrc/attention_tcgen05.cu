@@ -35,7 +35,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
 }
 
 struct TcAttnParams {
-  int H, Sq, Sk;
+  int H, Sq, Sk, causal;
   float scale_log2;     // scale * log2(e)
   float scale;
   float* lse;           // [B, H, Sq] or null
@@ -67,7 +67,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * TA_BQ;
   const int b = blockIdx.y / p.H, h = blockIdx.y % p.H;
-  const int n_kv = ceil_div(p.Sk, TA_BK);
+  // causal: keys beyond the last query of this tile are never attended to
+  const int n_kv = ceil_div(p.causal ? min(p.Sk, q0 + TA_BQ) : p.Sk, TA_BK);
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_o);
@@ -159,6 +160,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       tc_fence_after();
       const int kbase = j * TA_BK;
       const bool tail = kbase + TA_BK > p.Sk;
+      const bool diag = p.causal && (kbase + TA_BK - 1 > q0);   // some key of this tile lies after some query of the tile
       uint32_t v[128];
       tmem_ld_32x32(t_s, v);
       tmem_ld_32x32(t_s + 32, v + 32);
@@ -167,10 +169,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(s_empty);                                 // scores are in registers: QK^T of the next tile may start
-      if (tail) {
+      if (tail || diag) {
+        const int lim = diag ? min(p.Sk, q0 + row + 1) : p.Sk;   // first masked key index for this query row
 #pragma unroll
         for (int i = 0; i < 128; ++i)
-          if (kbase + i >= p.Sk) v[i] = __float_as_uint(-INFINITY);
+          if (kbase + i >= lim) v[i] = __float_as_uint(-INFINITY);
       }
       // row max with 8 independent chains (a single fmaxf chain would serialise 128 dependent 4-cycle ops)
       float mxp[8];
@@ -509,7 +512,6 @@ extern "C" int dwb_attention_fwd_tc(const void* q, int64_t ldq, const void* k, i
                                     int64_t ldo, float* lse, int B, int H, int Sq, int Sk, int head_dim, int causal, float scale,
                                     void* stream) {
   DWB_CHECK_ARG(head_dim == TA_HD, "dwb_attention_fwd_tc: head_dim %d unsupported (Whisper uses 64)", head_dim);
-  DWB_CHECK_ARG(!causal, "dwb_attention_fwd_tc: causal attention uses dwb_attention_fwd");
   DWB_CHECK_ARG(q && k && v && o, "dwb_attention_fwd_tc: null operand");
   DWB_CHECK_ARG(B > 0 && H > 0 && Sq > 0 && Sk > 0, "dwb_attention_fwd_tc: bad shape");
   CUtensorMap tq, tk, tv, to;
@@ -524,7 +526,7 @@ extern "C" int dwb_attention_fwd_tc(const void* q, int64_t ldq, const void* k, i
     attr = true;
   }
   TcAttnParams p;
-  p.H = H; p.Sq = Sq; p.Sk = Sk;
+  p.H = H; p.Sq = Sq; p.Sk = Sk; p.causal = causal;
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse;

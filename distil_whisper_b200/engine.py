@@ -389,7 +389,8 @@ def decoder_forward(st: _State, ids, enc, B, S, save):
         g, b_ = _ln(st, k + ".ln1", layer.self_attn_layer_norm)
         x1, h1, mu1, rs1 = ops.add_layernorm(x, y, g, b_, rows=M, d=d, save_stats=save)
         qkv = ops.gemm(h1, ws["wqkv"], bias=ws["bqkv"])
-        o1, lse1 = ops.attention_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], B, H, T, T, causal=True, need_lse=save)
+        o1, lse1 = ops.attention_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], B, H, T, T, causal=True, need_lse=save,
+                                     use_tc=USE_TC_ATTENTION)
         y1 = ops.gemm(o1, ws["wo"], bias=ws["bo"])
         # --- cross-attention over the encoder states
         wc = _attn_weights(st, k + ".ca", layer.encoder_attn, fuse_qkv=False)

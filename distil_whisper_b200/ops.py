@@ -76,12 +76,16 @@ def attention_fwd(q, k, v, B, H, Sq, Sk, causal, out=None, need_lse=True, use_tc
     return out, lse
 
 
-def attention_bwd(q, k, v, o, dout, lse, B, H, Sq, Sk, causal, dq_out, dk_out, dv_out):
+USE_TC_ATTENTION_BWD = True     # tcgen05 attention backward; False -> mma.sync kernel (cross-check)
+
+
+def attention_bwd(q, k, v, o, dout, lse, B, H, Sq, Sk, causal, dq_out, dk_out, dv_out, use_tc=None):
     """Writes dq_out/dk_out/dv_out (bf16 views with the layouts of q/k/v)."""
     dev = q.device
     delta = torch.empty((B * H * Sq,), dtype=F32, device=dev)
     dq_acc = torch.empty((B * Sq, H * HEAD_DIM), dtype=F32, device=dev)
-    _abi.call("dwb_attention_bwd", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(o), o.stride(0),
+    use_tc = USE_TC_ATTENTION_BWD if use_tc is None else use_tc
+    _abi.call("dwb_attention_bwd_tc" if use_tc else "dwb_attention_bwd", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(o), o.stride(0),
               _ptr(dout), dout.stride(0), _ptr(lse), _ptr(delta), _ptr(dq_acc), _ptr(dk_out), dk_out.stride(0), _ptr(dv_out),
               dv_out.stride(0), B, H, Sq, Sk, HEAD_DIM, int(causal), HEAD_DIM ** -0.5, _stream())
     cast_f32_to_bf16(dq_acc, dq_out)

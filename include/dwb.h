@@ -59,6 +59,11 @@ int dwb_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, co
                       const void* dout, int64_t lddo, const float* lse, float* delta_ws, float* dq_acc, void* dk, int64_t lddk,
                       void* dv, int64_t lddv, int B, int H, int Sq, int Sk, int head_dim, int causal, float scale, void* stream);
 
+/* Same contract on tcgen05 / TMEM (all five contractions of the flash-attention backward on the tensor core). */
+int dwb_attention_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o, int64_t ldo,
+                         const void* dout, int64_t lddo, const float* lse, float* delta_ws, float* dq_acc, void* dk, int64_t lddk,
+                         void* dv, int64_t lddv, int B, int H, int Sq, int Sk, int head_dim, int causal, float scale, void* stream);
+
 /* ---- residual add + LayerNorm ---------------------------------------------------------------------------------
  * x_new[r,:] = x_in[r % x_rows_mod (0: r), :] + y[r,:] (y bf16, nullable); ln = LayerNorm(x_new; gamma, beta, eps).
  * x_out (fp32), ln_out (bf16), mean/rstd (fp32 [rows]) are each optional.

@@ -74,6 +74,27 @@ def bench_attn():
     return out
 
 
+def bench_attn_bwd():
+    out = []
+    for (B, H, Sq, Sk, causal) in [(32, 20, 1500, 1500, 0), (32, 20, 128, 1500, 0), (32, 20, 128, 128, 1)]:
+        d = H * 64
+        q = torch.randn((B * Sq, d), device="cuda").bfloat16()
+        k = torch.randn((B * Sk, d), device="cuda").bfloat16()
+        v = torch.randn((B * Sk, d), device="cuda").bfloat16()
+        do = torch.randn((B * Sq, d), device="cuda").bfloat16()
+        o, lse = ops.attention_fwd(q, k, v, B, H, Sq, Sk, bool(causal), use_tc=not causal)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        fl = 10.0 * B * H * Sq * Sk * 64 * (0.5 if causal else 1.0)
+        row = dict(B=B, H=H, Sq=Sq, Sk=Sk, causal=causal)
+        for name, tc in (("tc", True), ("mma_sync", False)):
+            ms = timeit(lambda: ops.attention_bwd(q, k, v, o, do, lse, B, H, Sq, Sk, bool(causal), dq, dk, dv, use_tc=tc), iters=5)
+            row[name + "_ms"] = round(ms, 4)
+            row[name + "_tflops"] = round(fl / ms / 1e9, 1)
+        out.append(row)
+        print(row, flush=True)
+    return out
+
+
 def bench_logmel():
     """BASELINE.json configs[3]: 1024 x 480000-sample fp32 waveforms -> [1024, 80, 3000]; algorithmic bytes 2.88 MB / utterance."""
     from distil_whisper_b200.feature_extraction import WhisperFeatureExtractorB200
@@ -108,6 +129,8 @@ if __name__ == "__main__":
         res["gemm"] = bench_gemm()
     if "attn" in which:
         res["attn"] = bench_attn()
+    if "attn_bwd" in which:
+        res["attn_bwd"] = bench_attn_bwd()
     if "logmel" in which:
         res["logmel"] = bench_logmel()
     os.makedirs("gpurun_out", exist_ok=True)

@@ -24,6 +24,17 @@ elif kind == "attn":
     o = torch.empty((B * Sq, d), device="cuda", dtype=torch.bfloat16)
     for _ in range(3):
         ops.attention_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], B, H, Sq, Sk, bool(causal), out=o, use_tc=bool(tc))
+elif kind == "attn_bwd":
+    B, H, Sq, Sk, causal, tc = map(int, sys.argv[2:8])
+    d = H * 64
+    q = torch.randn((B * Sq, d), device="cuda").bfloat16()
+    k = torch.randn((B * Sk, d), device="cuda").bfloat16()
+    v = torch.randn((B * Sk, d), device="cuda").bfloat16()
+    do = torch.randn((B * Sq, d), device="cuda").bfloat16()
+    o, lse = ops.attention_fwd(q, k, v, B, H, Sq, Sk, bool(causal), use_tc=True)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    for _ in range(3):
+        ops.attention_bwd(q, k, v, o, do, lse, B, H, Sq, Sk, bool(causal), dq, dk, dv, use_tc=bool(tc))
 elif kind == "logmel":
     from distil_whisper_b200.feature_extraction import WhisperFeatureExtractorB200
     B = int(sys.argv[2])

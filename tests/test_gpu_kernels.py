@@ -51,36 +51,40 @@ def test_attention_fwd(ops, B, H, Sq, Sk, causal):
     assert torch.allclose(lse, lse_ref, atol=2e-3, rtol=1e-4)
 
 
+@pytest.mark.parametrize("causal", [False, True])
 @pytest.mark.parametrize("B,H,Sq,Sk", [(2, 2, 1500, 1500), (1, 3, 300, 300), (2, 2, 128, 128), (1, 1, 100, 700), (3, 20, 50, 50)])
-def test_attention_fwd_tcgen05(ops, B, H, Sq, Sk):
+def test_attention_fwd_tcgen05(ops, B, H, Sq, Sk, causal):
     """tcgen05 / TMEM encoder attention vs torch fp32 and vs the mma.sync kernel (same C-ABI contract)."""
     d = H * 64
     qkv = _randn((B * Sq, 3 * d), 11, 1.0, torch.bfloat16)
     kv = _randn((B * Sk, 2 * d), 12, 1.0, torch.bfloat16)
     q = qkv[:, :d]
     k, v = (qkv[:, d:2 * d], qkv[:, 2 * d:]) if Sq == Sk else (kv[:, :d], kv[:, d:])
-    o, lse = ops.attention_fwd(q, k, v, B, H, Sq, Sk, False, use_tc=True)
-    o_ref, lse_ref = _sdpa_ref(q, k, v, B, H, Sq, Sk, False)
+    o, lse = ops.attention_fwd(q, k, v, B, H, Sq, Sk, causal, use_tc=True)
+    o_ref, lse_ref = _sdpa_ref(q, k, v, B, H, Sq, Sk, causal)
     assert _rel(o, o_ref) < 8e-3, _rel(o, o_ref)
     assert torch.allclose(lse, lse_ref, atol=2e-3, rtol=1e-4)
-    o2, _ = ops.attention_fwd(q, k, v, B, H, Sq, Sk, False, use_tc=False)
+    o2, _ = ops.attention_fwd(q, k, v, B, H, Sq, Sk, causal, use_tc=False)
     assert _rel(o, o2.float()) < 8e-3
-    from distil_whisper_b200._abi import DwbError
-    with pytest.raises(DwbError):
-        ops.attention_fwd(q, k, v, B, H, Sq, Sk, True, use_tc=True)      # causal is the other kernel's job
 
 
+@pytest.mark.parametrize("use_tc", [True, False])
 @pytest.mark.parametrize("B,H,Sq,Sk,causal", [(2, 2, 128, 128, True), (1, 2, 12, 12, True), (2, 2, 100, 300, False),
-                                              (1, 1, 200, 1500, False), (2, 3, 70, 70, True)])
-def test_attention_bwd(ops, B, H, Sq, Sk, causal):
+                                              (1, 1, 200, 1500, False), (2, 3, 70, 70, True), (1, 2, 1500, 1500, False),
+                                              (2, 1, 300, 300, True), (1, 2, 50, 260, True)])
+def test_attention_bwd(ops, B, H, Sq, Sk, causal, use_tc):
+    """tcgen05 backward (use_tc) and the mma.sync backward against torch autograd of the fp32 reference."""
     d = H * 64
-    q = _randn((B * Sq, d), 3, 1.0, torch.bfloat16)
+    qkv = _randn((B * Sq, 3 * d), 3, 1.0, torch.bfloat16)            # strided views, like the fused QKV buffer
+    q = qkv[:, d:2 * d]
     k = _randn((B * Sk, d), 4, 1.0, torch.bfloat16)
     v = _randn((B * Sk, d), 5, 1.0, torch.bfloat16)
     dout = _randn((B * Sq, d), 6, 1.0, torch.bfloat16)
     o, lse = ops.attention_fwd(q, k, v, B, H, Sq, Sk, causal)
-    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-    ops.attention_bwd(q, k, v, o, dout, lse, B, H, Sq, Sk, causal, dq, dk, dv)
+    dq = torch.empty((B * Sq, d), dtype=torch.bfloat16, device="cuda")
+    dkv = torch.empty((B * Sk, 2 * d), dtype=torch.bfloat16, device="cuda")
+    dk, dv = dkv[:, :d], dkv[:, d:]
+    ops.attention_bwd(q, k, v, o, dout, lse, B, H, Sq, Sk, causal, dq, dk, dv, use_tc=use_tc)
     qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
     o_ref, _ = _sdpa_ref(qf, kf, vf, B, H, Sq, Sk, causal)
     o_ref.backward(dout.float())
