@@ -100,23 +100,29 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 4) {
-    // ===================================== TMA producer (one thread) ========================
-    if (lane == 0 && n_it > 0) {
-      mbar_expect_tx(kv_full, 2 * AB_TILE);
-      tma_load_3d(&tmap_k, kv_full, sK, h * AB_HD, k0, b);
-      tma_load_3d(&tmap_v, kv_full, sV, h * AB_HD, k0, b);
+    // ===================================== TMA producer (warp-uniform loop, elected lane issues) ==========
+    if (n_it > 0) {
+      const bool leader = elect_one();
+      if (leader) {
+        mbar_expect_tx(kv_full, 2 * AB_TILE);
+        tma_load_3d(&tmap_k, kv_full, sK, h * AB_HD, k0, b);
+        tma_load_3d(&tmap_v, kv_full, sV, h * AB_HD, k0, b);
+      }
       for (int it = 0; it < n_it; ++it) {
         const int st = it & 1;
         mbar_wait(&q_empty[st], ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(&q_full[st], 2 * AB_TILE);
-        tma_load_3d(&tmap_q, &q_full[st], sQ + st * AB_TILE, h * AB_HD, (i0 + it) * AB_T, b);
-        tma_load_3d(&tmap_do, &q_full[st], sDO + st * AB_TILE, h * AB_HD, (i0 + it) * AB_T, b);
+        if (leader) {
+          mbar_expect_tx(&q_full[st], 2 * AB_TILE);
+          tma_load_3d(&tmap_q, &q_full[st], sQ + st * AB_TILE, h * AB_HD, (i0 + it) * AB_T, b);
+          tma_load_3d(&tmap_do, &q_full[st], sDO + st * AB_TILE, h * AB_HD, (i0 + it) * AB_T, b);
+        }
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else if (warp == 5) {
-    // ===================================== MMA issuer (one thread) ==========================
-    if (lane == 0 && n_it > 0) {
+    // ===================================== MMA issuer (warp-uniform loop, elected lane issues) ============
+    if (n_it > 0) {
+      const bool leader = elect_one();
       constexpr uint32_t id_nn = umma_idesc_bf16(128, 128, 0, 0);     // S^T, dP^T
       constexpr uint32_t id_kb = umma_idesc_bf16(128, 64, 0, 1);      // dV (TS), dK: K-major A, MN-major B
       constexpr uint32_t id_mm = umma_idesc_bf16(128, 64, 1, 1);      // dQ: MN-major A and B
@@ -131,13 +137,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         mbar_wait(&q_full[st], (it >> 1) & 1);
         mbar_wait(sdp_empty, (it & 1) ^ 1);
         tc_fence_after();
-        const uint64_t dQ_k = umma_desc_sw128(smem_u32(sQ + st * AB_TILE), 16, 1024);
-        const uint64_t dDO_k = umma_desc_sw128(smem_u32(sDO + st * AB_TILE), 16, 1024);
+        if (leader) {
+          const uint64_t dQ_k = umma_desc_sw128(smem_u32(sQ + st * AB_TILE), 16, 1024);
+          const uint64_t dDO_k = umma_desc_sw128(smem_u32(sDO + st * AB_TILE), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_ss(tmem_base + AB_TM_S, dK_k + (uint64_t)(2 * k), dQ_k + (uint64_t)(2 * k), id_nn, k > 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) tc_mma_ss(tmem_base + AB_TM_S, dK_k + (uint64_t)(2 * k), dQ_k + (uint64_t)(2 * k), id_nn, k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_ss(tmem_base + AB_TM_DP, dV_k + (uint64_t)(2 * k), dDO_k + (uint64_t)(2 * k), id_nn, k > 0 ? 1u : 0u);
-        tc_commit(sdp_full);
+          for (int k = 0; k < 4; ++k) tc_mma_ss(tmem_base + AB_TM_DP, dV_k + (uint64_t)(2 * k), dDO_k + (uint64_t)(2 * k), id_nn, k > 0 ? 1u : 0u);
+          tc_commit(sdp_full);
+        }
+        __syncwarp();
       };
       issue_sdp(0);
       for (int it = 0; it < n_it; ++it) {
@@ -147,25 +156,30 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         tc_fence_after();
         const uint64_t dQ_mn = umma_desc_sw128(smem_u32(sQ + st * AB_TILE), AB_TILE, 1024);
         const uint64_t dDO_mn = umma_desc_sw128(smem_u32(sDO + st * AB_TILE), AB_TILE, 1024);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)     // dV += P^T dO_i      (K = 128 queries, 16 per step = 8 TMEM columns / 2048 B of dO)
-          tc_mma_ts(tmem_base + AB_TM_DV, tmem_base + AB_TM_P + 8 * k, dDO_mn + (uint64_t)(k * 128), id_kb, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 8; ++k)     // dV += P^T dO_i      (K = 128 queries, 16 per step = 8 TMEM columns / 2048 B of dO)
+            tc_mma_ts(tmem_base + AB_TM_DV, tmem_base + AB_TM_P + 8 * k, dDO_mn + (uint64_t)(k * 128), id_kb, (it > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)     // dK += dS^T Q_i
-          tc_mma_ss(tmem_base + AB_TM_DK, dDS_k + (uint64_t)((k >> 2) * (AB_TILE >> 4) + 2 * (k & 3)), dQ_mn + (uint64_t)(k * 128), id_kb,
-                    (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 8; ++k)     // dK += dS^T Q_i
+            tc_mma_ss(tmem_base + AB_TM_DK, dDS_k + (uint64_t)((k >> 2) * (AB_TILE >> 4) + 2 * (k & 3)), dQ_mn + (uint64_t)(k * 128), id_kb,
+                      (it > 0 || k > 0) ? 1u : 0u);
+        }
+        __syncwarp();
         mbar_wait(dq_empty, (it & 1) ^ 1);   // the compute threads drain tile it-1's dQ while dV / dK above run
         tc_fence_after();
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)     // dQ_i = dS K_j       (K = 128 keys)
-          tc_mma_ss(tmem_base + AB_TM_DQ, dDS_mn + (uint64_t)(k * 128), dK_mn + (uint64_t)(k * 128), id_mm, k > 0 ? 1u : 0u);
-        tc_commit(dq_full);
-        tc_commit(&q_empty[st]);
-        tc_commit(pds_empty);
+          for (int k = 0; k < 8; ++k)     // dQ_i = dS K_j       (K = 128 keys)
+            tc_mma_ss(tmem_base + AB_TM_DQ, dDS_mn + (uint64_t)(k * 128), dK_mn + (uint64_t)(k * 128), id_mm, k > 0 ? 1u : 0u);
+          tc_commit(dq_full);
+          tc_commit(&q_empty[st]);
+          tc_commit(pds_empty);
+        }
+        __syncwarp();
       }
-      tc_commit(acc_full);
+      if (leader) tc_commit(acc_full);
     }
-    __syncwarp();
   } else {
     // ===================================== compute: one thread per key row ==================
     const int row = warp * 32 + lane;                 // key row inside the tile == TMEM lane

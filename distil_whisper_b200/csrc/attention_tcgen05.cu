@@ -96,23 +96,29 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
   }
   if (warp == 4) {
-    // ===================================== TMA producer (one thread) ========================
-    if (lane == 0) {
-      mbar_expect_tx(q_full, TA_TILE_BYTES);
-      tma_load_3d(&tmap_q, q_full, sQ, h * TA_HD, q0, b);
+    // ===================================== TMA producer (warp-uniform loop, elected lane issues) ==========
+    {
+      const bool leader = elect_one();
+      if (leader) {
+        mbar_expect_tx(q_full, TA_TILE_BYTES);
+        tma_load_3d(&tmap_q, q_full, sQ, h * TA_HD, q0, b);
+      }
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % TA_KV_STAGES;
         mbar_wait(&kv_empty[st], ((j / TA_KV_STAGES) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[st], 2 * TA_TILE_BYTES);
-        tma_load_3d(&tmap_k, &kv_full[st], sKV + st * 2 * TA_TILE_BYTES, h * TA_HD, j * TA_BK, b);
-        tma_load_3d(&tmap_v, &kv_full[st], sKV + st * 2 * TA_TILE_BYTES + TA_TILE_BYTES, h * TA_HD, j * TA_BK, b);
+        if (leader) {
+          mbar_expect_tx(&kv_full[st], 2 * TA_TILE_BYTES);
+          tma_load_3d(&tmap_k, &kv_full[st], sKV + st * 2 * TA_TILE_BYTES, h * TA_HD, j * TA_BK, b);
+          tma_load_3d(&tmap_v, &kv_full[st], sKV + st * 2 * TA_TILE_BYTES + TA_TILE_BYTES, h * TA_HD, j * TA_BK, b);
+        }
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else if (warp == 5) {
-    // ===================================== MMA issuer (one thread) ==========================
-    // issue order: QK(0), then per tile j: QK(j+1) (as soon as tile j's scores have left TMEM), PV(j) (once P_j is in smem)
-    if (lane == 0) {
+    // ===================================== MMA issuer (warp-uniform loop, elected lane issues) ============
+    // issue order: QK(0), then per tile j: QK(j+1) (as soon as tile j's scores have left TMEM), PV(j) (once P_j is in TMEM)
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
       mbar_wait(q_full, 0);
@@ -122,10 +128,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         mbar_wait(&kv_full[st], (j / TA_KV_STAGES) & 1);
         mbar_wait(s_empty, (j & 1) ^ 1);
         tc_fence_after();
-        const uint64_t dk = umma_desc_sw128(smem_u32(sKV + st * 2 * TA_TILE_BYTES), 16, 1024);
+        if (leader) {
+          const uint64_t dk = umma_desc_sw128(smem_u32(sKV + st * 2 * TA_TILE_BYTES), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < TA_HD / 16; ++k) tc_mma_ss(tmem_s, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_qk, k > 0 ? 1u : 0u);
-        tc_commit(s_full);
+          for (int k = 0; k < TA_HD / 16; ++k) tc_mma_ss(tmem_s, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_qk, k > 0 ? 1u : 0u);
+          tc_commit(s_full);
+        }
+        __syncwarp();
       };
       issue_qk(0);
       for (int j = 0; j < n_kv; ++j) {
@@ -133,16 +142,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         if (j + 1 < n_kv) issue_qk(j + 1);
         mbar_wait(p_full, j & 1);                  // P_j is in TMEM (and any rescale of O finished)
         tc_fence_after();
-        const uint64_t dv = umma_desc_sw128(smem_u32(sKV + st * 2 * TA_TILE_BYTES + TA_TILE_BYTES), TA_TILE_BYTES, 1024);
+        if (leader) {
+          const uint64_t dv = umma_desc_sw128(smem_u32(sKV + st * 2 * TA_TILE_BYTES + TA_TILE_BYTES), TA_TILE_BYTES, 1024);
 #pragma unroll
-        for (int k = 0; k < TA_BK / 16; ++k)       // A = P from TMEM: 16 keys = 8 columns per step; O accumulates in TMEM
-          tc_mma_ts(tmem_o, tmem_p + 8 * k, dv + (uint64_t)(k * 128), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-        tc_commit(o_full);
-        tc_commit(&kv_empty[st]);
-        tc_commit(p_empty);
+          for (int k = 0; k < TA_BK / 16; ++k)       // A = P from TMEM: 16 keys = 8 columns per step; O accumulates in TMEM
+            tc_mma_ts(tmem_o, tmem_p + 8 * k, dv + (uint64_t)(k * 128), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          tc_commit(o_full);
+          tc_commit(&kv_empty[st]);
+          tc_commit(p_empty);
+        }
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else if (warp < 4) {
     // ===================================== softmax / output =================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
@@ -215,8 +226,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         uint32_t pk[32];
 #pragma unroll
         for (int i = 0; i < 64; i += 2) {
-          const float e0 = fast_exp2(fmaf(__uint_as_float(v[c * 64 + i]), p.scale_log2, -msc));
-          const float e1 = fast_exp2(fmaf(__uint_as_float(v[c * 64 + i + 1]), p.scale_log2, -msc));
+          const float a0 = fmaf(__uint_as_float(v[c * 64 + i]), p.scale_log2, -msc);
+          const float a1 = fmaf(__uint_as_float(v[c * 64 + i + 1]), p.scale_log2, -msc);
+          const float e0 = fast_exp2(a0);
+          const float e1 = ((i & 6) == 6) ? poly_exp2(a1) : fast_exp2(a1);   // 1 exponential in 8 on the FMA pipe
           ls[(i >> 1) & 3] += e0 + e1;
           pk[i >> 1] = pack_bf16x2(e0, e1);
         }

@@ -99,8 +99,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 4) {
-    // ===================================== TMA producer (one thread) ========================
-    if (lane == 0) {
+    // ===================================== TMA producer ======================================
+    // The whole warp walks the loop (uniform control flow); elect.sync picks the issuing lane, which lets ptxas emit the
+    // UTMALDG / UTCHMMA instructions directly instead of wrapping each one in a per-thread election loop.
+    {
+      const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -112,31 +115,35 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int kb1 = min(kb0 + kb_per_split, num_kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          if (A_MN) {
+          if (leader) {
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + Cfg::kABytes;
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            if (A_MN) {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(&tmap_a, &full_bar[stage], sa + j * (BK * 128), m0 + 64 * j, kb * BK);
-          } else {
-            tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BK, m0);
-          }
-          if (B_MN) {
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d(&tmap_a, &full_bar[stage], sa + j * (BK * 128), m0 + 64 * j, kb * BK);
+            } else {
+              tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BK, m0);
+            }
+            if (B_MN) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(&tmap_b, &full_bar[stage], sb + j * (BK * 128), n0 + 64 * j, kb * BK);
-          } else {
-            tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * BK, n0);
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(&tmap_b, &full_bar[stage], sb + j * (BK * 128), n0 + 64 * j, kb * BK);
+            } else {
+              tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * BK, n0);
+            }
           }
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 5) {
-    // ===================================== MMA issuer (one thread) ==========================
+    // ===================================== MMA issuer ========================================
     // Highest warp id in the CTA: the SMSP arbiter favours it over the epilogue warp sharing its sub-partition, so
     // epilogue math never delays tensor-core issue.
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
       // descriptor start-address advance (16 B units) per UMMA_K = 16 elements of K
       constexpr uint32_t a_kstep = A_MN ? (2 * 1024) >> 4 : 32 >> 4;
@@ -160,17 +167,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = da0 + (uint64_t)(stage * (Cfg::kStageBytes >> 4));
-          const uint64_t db = db0 + (uint64_t)(stage * (Cfg::kStageBytes >> 4));
+          if (leader) {
+            const uint64_t da = da0 + (uint64_t)(stage * (Cfg::kStageBytes >> 4));
+            const uint64_t db = db0 + (uint64_t)(stage * (Cfg::kStageBytes >> 4));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            tc_mma_ss(tmem_d, da + (uint64_t)(k * a_kstep), db + (uint64_t)(k * b_kstep), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              tc_mma_ss(tmem_d, da + (uint64_t)(k * a_kstep), db + (uint64_t)(k * b_kstep), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit(&empty_bar[stage]);             // frees the smem stage once these MMAs retire
+            if (kb == kb1 - 1) tc_commit(&tmem_full[acc]);
           }
-          tc_commit(&empty_bar[stage]);             // frees the smem stage once these MMAs retire
-          if (kb == kb1 - 1) tc_commit(&tmem_full[acc]);
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        if (kb1 <= kb0) tc_commit(&tmem_full[acc]);   // empty K slice (never with sane split_k)
+        if (kb1 <= kb0 && leader) tc_commit(&tmem_full[acc]);   // empty K slice (never with sane split_k)
       }
     }
     __syncwarp();

@@ -79,11 +79,12 @@ logmel_kernel(const LogmelPlan plan, const float* __restrict__ wav, float* __res
   float2* s_tw200 = reinterpret_cast<float2*>(s_window + LM_NFFT);                 // [200]
   float2* s_tw25 = s_tw200 + 200;                                                  // [25] (+1 pad)
   float2* s_tw400 = s_tw25 + 26;                                                   // [201] (+1 pad)
-  float* s_samples = reinterpret_cast<float*>(s_tw400 + 202);                      // [(F-1)*160 + 400]
+  float* s_melw = reinterpret_cast<float*>(s_tw400 + 202);                         // [n_mels][wp]  (wp odd: conflict-free)
+  const int wp = plan.max_w | 1;
+  float* s_samples = s_melw + (((size_t)n_mels * wp + 3) & ~(size_t)3);            // [(F-1)*160 + 400]
   const int span_max = (F - 1) * LM_HOP + LM_NFFT;
   float2* bufA = reinterpret_cast<float2*>(s_samples + span_max);                  // [F][200]
   float2* bufB = bufA + (size_t)F * 200;                                           // [F][200]  (aliased by pow [F][203])
-  float* s_pow = reinterpret_cast<float*>(bufB);
   __shared__ float s_red[LM_THREADS / 32];
   __shared__ float s_cta_max;
 
@@ -98,6 +99,15 @@ logmel_kernel(const LogmelPlan plan, const float* __restrict__ wav, float* __res
   for (int i = tid; i < 200; i += LM_THREADS) s_tw200[i] = plan.d_tw200[i];
   for (int i = tid; i < 25; i += LM_THREADS) s_tw25[i] = plan.d_tw25[i];
   for (int i = tid; i < LM_NFREQ; i += LM_THREADS) s_tw400[i] = plan.d_tw400[i];
+  for (int i = tid; i < n_mels * plan.max_w; i += LM_THREADS) s_melw[(i / plan.max_w) * wp + (i % plan.max_w)] = plan.d_mel_w[i];
+  // this lane's mel filters (m = lane + 32 i): first bin and width, kept in registers for the whole kernel
+  int mel_st[4], mel_cnt[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = (tid & 31) + 32 * i;
+    mel_st[i] = m < n_mels ? __ldg(plan.d_mel_start + m) : 0;
+    mel_cnt[i] = m < n_mels ? __ldg(plan.d_mel_count + m) : 0;
+  }
 
   float lmax = -INFINITY;
   for (int f0 = f_begin; f0 < f_end; f0 += F) {
@@ -113,87 +123,112 @@ logmel_kernel(const LogmelPlan plan, const float* __restrict__ wav, float* __res
       s_samples[i] = __ldg(w + o);
     }
     __syncthreads();
-    // ---- 2. radix-8 over n1 (z[25 n1 + n2]), twiddle W200^(n2 k1) ----
-    for (int it = tid; it < nf * 25; it += LM_THREADS) {
-      const int f = it / 25, n2 = it - f * 25;
-      const float* xs = s_samples + f * LM_HOP + 2 * n2;
-      const float* ws = s_window + 2 * n2;
-      float2 x[8];
+    // ---- per-frame pipeline: each warp owns whole frames (f = warp, warp+16, ...), stages separated by __syncwarp only ----
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int f = warp; f < nf; f += LM_THREADS / 32) {
+      float2* zA = bufA + (size_t)f * 200;
+      float2* zB = bufB + (size_t)f * 200;
+      float* pw = reinterpret_cast<float*>(zB);           // power spectrum of this frame (after stage 4 has consumed zB)
+      // -- 2. radix-8 over n1 (z[25 n1 + n2]), twiddle W200^(n2 k1): lanes 0..24
+      if (lane < 25) {
+        const int n2 = lane;
+        const float* xs = s_samples + f * LM_HOP + 2 * n2;
+        const float* ws = s_window + 2 * n2;
+        float2 x[8];
 #pragma unroll
-      for (int n1 = 0; n1 < 8; ++n1) {
-        const float2 sv = *reinterpret_cast<const float2*>(xs + 50 * n1);
-        const float2 wv = *reinterpret_cast<const float2*>(ws + 50 * n1);
-        x[n1] = make_float2(sv.x * wv.x, sv.y * wv.y);
+        for (int n1 = 0; n1 < 8; ++n1) {
+          const float2 sv = *reinterpret_cast<const float2*>(xs + 50 * n1);
+          const float2 wv = *reinterpret_cast<const float2*>(ws + 50 * n1);
+          x[n1] = make_float2(sv.x * wv.x, sv.y * wv.y);
+        }
+        float2 a0 = cadd(x[0], x[4]), a1 = cadd(x[1], x[5]), a2 = cadd(x[2], x[6]), a3 = cadd(x[3], x[7]);
+        float2 b0 = csub(x[0], x[4]), b1 = csub(x[1], x[5]), b2 = csub(x[2], x[6]), b3 = csub(x[3], x[7]);
+        const float r = 0.70710678118654752f;
+        b1 = make_float2((b1.x + b1.y) * r, (b1.y - b1.x) * r);      // * W8^1 = (1 - i)/sqrt2
+        b2 = mul_mi(b2);                                              // * W8^2 = -i
+        b3 = make_float2((b3.y - b3.x) * r, -(b3.x + b3.y) * r);     // * W8^3 = (-1 - i)/sqrt2
+        dft4(a0, a1, a2, a3);   // X[0], X[2], X[4], X[6]
+        dft4(b0, b1, b2, b3);   // X[1], X[3], X[5], X[7]
+        float2* dst = zA + n2;
+        dst[0] = a0;
+        dst[25] = cmul(b0, s_tw200[n2]);
+        dst[50] = cmul(a1, s_tw200[2 * n2]);
+        dst[75] = cmul(b1, s_tw200[3 * n2]);
+        dst[100] = cmul(a2, s_tw200[4 * n2]);
+        dst[125] = cmul(b2, s_tw200[5 * n2]);
+        dst[150] = cmul(a3, s_tw200[6 * n2]);
+        dst[175] = cmul(b3, s_tw200[7 * n2]);
       }
-      float2 a0 = cadd(x[0], x[4]), a1 = cadd(x[1], x[5]), a2 = cadd(x[2], x[6]), a3 = cadd(x[3], x[7]);
-      float2 b0 = csub(x[0], x[4]), b1 = csub(x[1], x[5]), b2 = csub(x[2], x[6]), b3 = csub(x[3], x[7]);
-      const float r = 0.70710678118654752f;
-      b1 = make_float2((b1.x + b1.y) * r, (b1.y - b1.x) * r);      // * W8^1 = (1 - i)/sqrt2
-      b2 = mul_mi(b2);                                              // * W8^2 = -i
-      b3 = make_float2((b3.y - b3.x) * r, -(b3.x + b3.y) * r);     // * W8^3 = (-1 - i)/sqrt2
-      dft4(a0, a1, a2, a3);   // X[0], X[2], X[4], X[6]
-      dft4(b0, b1, b2, b3);   // X[1], X[3], X[5], X[7]
-      float2* dst = bufA + (size_t)f * 200 + n2;
-      dst[0] = a0;
-      dst[25] = cmul(b0, s_tw200[n2]);
-      dst[50] = cmul(a1, s_tw200[2 * n2]);
-      dst[75] = cmul(b1, s_tw200[3 * n2]);
-      dst[100] = cmul(a2, s_tw200[4 * n2]);
-      dst[125] = cmul(b2, s_tw200[5 * n2]);
-      dst[150] = cmul(a3, s_tw200[6 * n2]);
-      dst[175] = cmul(b3, s_tw200[7 * n2]);
-    }
-    __syncthreads();
-    // ---- 3. DFT-25 = 5 x 5: first radix-5 over a (n2 = 5a + b), twiddle W25^(b c) ----
-    for (int it = tid; it < nf * 40; it += LM_THREADS) {
-      const int f = it / 40, r = it - f * 40, k1 = r / 5, bb = r - k1 * 5;
-      const float2* src = bufA + (size_t)f * 200 + k1 * 25 + bb;
-      float2 y0 = src[0], y1 = src[5], y2 = src[10], y3 = src[15], y4 = src[20];
-      dft5(y0, y1, y2, y3, y4);
-      float2* dst = bufB + (size_t)f * 200 + k1 * 25 + bb * 5;
-      dst[0] = y0;
-      dst[1] = cmul(y1, s_tw25[bb]);
-      dst[2] = cmul(y2, s_tw25[2 * bb]);
-      dst[3] = cmul(y3, s_tw25[3 * bb]);
-      dst[4] = cmul(y4, s_tw25[4 * bb]);
-    }
-    __syncthreads();
-    // ---- 4. second radix-5 over b -> Z[k1 + 8 (c + 5 e)] ----
-    for (int it = tid; it < nf * 40; it += LM_THREADS) {
-      const int f = it / 40, r = it - f * 40, k1 = r / 5, c = r - k1 * 5;
-      const float2* src = bufB + (size_t)f * 200 + k1 * 25 + c;
-      float2 u0 = src[0], u1 = src[5], u2 = src[10], u3 = src[15], u4 = src[20];
-      dft5(u0, u1, u2, u3, u4);
-      float2* dst = bufA + (size_t)f * 200 + k1 + 8 * c;
-      dst[0] = u0; dst[40] = u1; dst[80] = u2; dst[120] = u3; dst[160] = u4;
-    }
-    __syncthreads();
-    // ---- 5. real-FFT split + power spectrum ----
-    for (int it = tid; it < nf * LM_NFREQ; it += LM_THREADS) {
-      const int f = it / LM_NFREQ, k = it - f * LM_NFREQ;
-      const float2* z = bufA + (size_t)f * 200;
-      const float2 zk = z[k == 200 ? 0 : k];
-      float2 zr = z[k == 0 ? 0 : 200 - k];
-      zr.y = -zr.y;
-      const float2 e = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y + zr.y));
-      const float2 d = make_float2(0.5f * (zk.x - zr.x), 0.5f * (zk.y - zr.y));
-      const float2 o = mul_mi(d);
-      const float2 t = cmul(o, s_tw400[k]);
-      const float re = e.x + t.x, im = e.y + t.y;
-      s_pow[f * LM_POW_PITCH + k] = re * re + im * im;
-    }
-    __syncthreads();
-    // ---- 6. mel projection + log10 ----
-    for (int it = tid; it < nf * n_mels; it += LM_THREADS) {
-      const int m = it / nf, f = it - m * nf;
-      const int st = __ldg(plan.d_mel_start + m), cnt = __ldg(plan.d_mel_count + m);
-      const float* wrow = plan.d_mel_w + (size_t)m * plan.max_w;
-      const float* prow = s_pow + f * LM_POW_PITCH + st;
-      float acc = 0.f;
-      for (int j = 0; j < cnt; ++j) acc = fmaf(__ldg(wrow + j), prow[j], acc);
-      const float lv = log10f(fmaxf(acc, 1e-10f));
-      out_s[(size_t)m * frames_per_cta + (f0 - f_begin) + f] = lv;
-      lmax = fmaxf(lmax, lv);
+      __syncwarp();
+      // -- 3. DFT-25 = 5 x 5: radix-5 over a (n2 = 5a + b), twiddle W25^(b c); 40 items = lanes 0..31 then 0..7
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int r = pass * 32 + lane;
+        if (r < 40) {
+          const int k1 = r / 5, bb = r - k1 * 5;
+          const float2* src = zA + k1 * 25 + bb;
+          float2 y0 = src[0], y1 = src[5], y2 = src[10], y3 = src[15], y4 = src[20];
+          dft5(y0, y1, y2, y3, y4);
+          float2* dst = zB + k1 * 25 + bb * 5;
+          dst[0] = y0;
+          dst[1] = cmul(y1, s_tw25[bb]);
+          dst[2] = cmul(y2, s_tw25[2 * bb]);
+          dst[3] = cmul(y3, s_tw25[3 * bb]);
+          dst[4] = cmul(y4, s_tw25[4 * bb]);
+        }
+      }
+      __syncwarp();
+      // -- 4. second radix-5 over b -> Z[k1 + 8 (c + 5 e)]
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int r = pass * 32 + lane;
+        if (r < 40) {
+          const int k1 = r / 5, c = r - k1 * 5;
+          const float2* src = zB + k1 * 25 + c;
+          float2 u0 = src[0], u1 = src[5], u2 = src[10], u3 = src[15], u4 = src[20];
+          dft5(u0, u1, u2, u3, u4);
+          float2* dst = zA + k1 + 8 * c;
+          dst[0] = u0; dst[40] = u1; dst[80] = u2; dst[120] = u3; dst[160] = u4;
+        }
+      }
+      __syncwarp();
+      // -- 5. real-FFT split + power spectrum, bins k and 200-k together (X[k] = E + W^k O, conj X[200-k] = E - W^k O)
+#pragma unroll
+      for (int pass = 0; pass < 4; ++pass) {
+        const int k = pass * 32 + lane;                    // 0..100
+        if (k <= 100) {
+          const float2 zk = zA[k];
+          float2 zr = zA[k == 0 ? 0 : 200 - k];
+          zr.y = -zr.y;
+          const float2 e = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y + zr.y));
+          const float2 d = make_float2(0.5f * (zk.x - zr.x), 0.5f * (zk.y - zr.y));
+          const float2 t = cmul(mul_mi(d), s_tw400[k]);
+          const float re0 = e.x + t.x, im0 = e.y + t.y, re1 = e.x - t.x, im1 = e.y - t.y;
+          pw[k] = re0 * re0 + im0 * im0;
+          pw[200 - k] = re1 * re1 + im1 * im1;             // k = 100 writes the same bin twice with the same value
+        }
+      }
+      __syncwarp();
+      // -- 6. mel projection + log10: lanes over mel bins
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = lane + 32 * i;
+        if (m < n_mels) {
+          const float* wrow = s_melw + m * wp;
+          const float* prow = pw + mel_st[i];
+          float acc0 = 0.f, acc1 = 0.f;
+          int j = 0;
+          for (; j + 1 < mel_cnt[i]; j += 2) {
+            acc0 = fmaf(wrow[j], prow[j], acc0);
+            acc1 = fmaf(wrow[j + 1], prow[j + 1], acc1);
+          }
+          if (j < mel_cnt[i]) acc0 = fmaf(wrow[j], prow[j], acc0);
+          const float lv = log10f(fmaxf(acc0 + acc1, 1e-10f));
+          out_s[(size_t)m * frames_per_cta + (f0 - f_begin) + f] = lv;
+          lmax = fmaxf(lmax, lv);
+        }
+      }
+      __syncwarp();
     }
   }
   // ---- per-utterance max through distributed shared memory ----
@@ -293,7 +328,8 @@ extern "C" int dwb_logmel(void* plan_v, const float* wav, int B, int n_samples, 
   const int n_frames = n_samples / LM_HOP;
   int fpc = ceil_div(n_frames, LM_CLUSTER);
   fpc = (fpc + 3) & ~3;
-  const size_t fixed = (size_t)p->n_mels * fpc * 4 + LM_NFFT * 4 + (200 + 26 + 202) * 8 + (LM_NFFT - LM_HOP) * 4 + 256;
+  const size_t fixed = (size_t)p->n_mels * fpc * 4 + LM_NFFT * 4 + (200 + 26 + 202) * 8 + (LM_NFFT - LM_HOP) * 4 + 256 +
+                       ((size_t)p->n_mels * (p->max_w | 1) + 4) * 4;
   const size_t per_frame = LM_HOP * 4 + 2 * 200 * 8;   // samples + bufA + bufB (pow aliases bufB: 203*4 <= 1600)
   const size_t budget = 227 * 1024;
   DWB_CHECK_ARG(fixed + per_frame <= budget, "dwb_logmel: slab for n_mels=%d x %d frames does not fit in shared memory", p->n_mels, fpc);
