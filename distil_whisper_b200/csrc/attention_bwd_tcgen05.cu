@@ -3,7 +3,7 @@
 //   flash-attention backward run on the tensor core, transposed so that TMEM lanes are KEY rows:
 //     S^T  = K_j Q_i^T          (SS, 128x128x64)   -> TMEM [  0,128)
 //     dP^T = V_j dO_i^T         (SS, 128x128x64)   -> TMEM [128,256)
-//     P^T  = exp2(S^T c - lse_q),  dS^T = P^T (dP^T - delta_q) scale      (one thread per key row, fp32)
+//     P^T  = exp2(S^T c - lse_q),  dS^T = P^T (dP^T - delta_q) scale      (two threads per key row, 64 query columns each, fp32)
 //     dV_j += P^T  dO_i         (TS: P^T from TMEM [256,320) as bf16 pairs; dO_i is the MN-major B operand)   -> TMEM [320,384)
 //     dK_j += dS^T Q_i          (SS: dS^T tile in smem, K-major A; Q_i MN-major B)                            -> TMEM [384,448)
 //     dQ_i  = dS   K_j          (SS: the SAME smem tile read as an MN-major A operand; K_j MN-major B)        -> TMEM [448,512)
@@ -19,7 +19,7 @@ namespace dwb {
 constexpr int AB_T = 128;                   // tile edge (queries and keys)
 constexpr int AB_HD = 64;
 constexpr int AB_TILE = 128 * 128;          // bytes of a [128 x 64] bf16 tile
-constexpr int AB_THREADS = 192;             // warps 0-3 compute (one thread per key row), warp 4 TMA, warp 5 MMA
+constexpr int AB_THREADS = 384;             // warps 0-7 compute (two threads per key row: 64 query columns each), warp 8 TMA, warp 9 MMA
 constexpr int AB_OFF_K = 0, AB_OFF_V = AB_TILE, AB_OFF_Q = 2 * AB_TILE /*2 stages*/, AB_OFF_DO = 4 * AB_TILE /*2 stages*/,
               AB_OFF_DS = 6 * AB_TILE /*2 halves*/, AB_OFF_DQ = 8 * AB_TILE /*fp32 staging, 2 panels of 16 KB*/,
               AB_OFF_END = 10 * AB_TILE;
@@ -79,18 +79,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const int i0 = p.causal ? min(k0 / AB_T, n_q) : 0;     // first query tile that sees this key tile
   const int n_it = n_q - i0;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
     tma_prefetch_desc(&tmap_dq); tma_prefetch_desc(&tmap_dk); tma_prefetch_desc(&tmap_dv);
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
-    mbar_init(sdp_full, 1); mbar_init(sdp_empty, 128);
-    mbar_init(pds_full, 128); mbar_init(pds_empty, 1);
-    mbar_init(dq_full, 1); mbar_init(dq_empty, 128);
+    mbar_init(sdp_full, 1); mbar_init(sdp_empty, 256);
+    mbar_init(pds_full, 256); mbar_init(pds_empty, 1);
+    mbar_init(dq_full, 1); mbar_init(dq_empty, 256);
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(tmem_ptr, 512);
     tmem_relinquish();
   }
@@ -99,7 +99,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================================== TMA producer (warp-uniform loop, elected lane issues) ==========
     if (n_it > 0) {
       const bool leader = elect_one();
@@ -119,7 +119,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         __syncwarp();
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================================== MMA issuer (warp-uniform loop, elected lane issues) ============
     if (n_it > 0) {
       const bool leader = elect_one();
@@ -180,12 +180,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       }
       if (leader) tc_commit(acc_full);
     }
-  } else {
-    // ===================================== compute: one thread per key row ==================
-    const int row = warp * 32 + lane;                 // key row inside the tile == TMEM lane
+  } else if (warp < 8) {
+    // ===================================== compute: two threads per key row =================
+    const int wq = warp & 3, hsel = warp >> 2;       // TMEM lane quadrant, and which 64 query columns this thread owns
+    const int row = wq * 32 + lane;                   // key row inside the tile == TMEM lane
     const int key = k0 + row;
     const bool key_ok = key < p.Sk;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     const uint32_t sDS_row = smem_u32(sDS) + row * 128;
     const uint32_t sDQ_row = smem_u32(sDQ) + row * 128;
     const int sw = row & 7;
@@ -197,22 +198,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       mbar_wait(dq_full, t & 1);
       tc_fence_after();
       if (threadIdx.x == 0) tma_store_wait_read<0>();           // previous reduce-add has left the staging panels
-      named_bar_sync(2, 128);
-#pragma unroll
-      for (int pnl = 0; pnl < 2; ++pnl) {
+      named_bar_sync(2, 256);
+      {
+        const int pnl = hsel;                                   // this warpgroup's 32 fp32 columns
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + AB_TM_DQ + lane_off + pnl * 32, v);
         tmem_ld_wait();
-        if (pnl == 1) {
-          tc_fence_before();
-          mbar_arrive(dq_empty);
-        }
+        tc_fence_before();
+        mbar_arrive(dq_empty);
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch)
           st_shared_v4(sDQ_row + pnl * AB_TILE + ((ch ^ sw) << 4), v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
       }
       fence_proxy_async_smem();
-      named_bar_sync(3, 128);
+      named_bar_sync(3, 256);
       if (threadIdx.x == 0) {
         const int tq0 = (i0 + t) * AB_T;
         tma_reduce_add_3d(&tmap_dq, sDQ, h * AB_HD, tq0, b);
@@ -231,25 +230,27 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       const int q0 = (i0 + it) * AB_T;
       // per-query constants of this tile: lse (in log2 units) and delta; +inf lse zeroes padded query columns.
       // They were fetched one iteration ahead (pre_lse / pre_del), so the global-load latency is off the critical path.
-      sLse[st * 128 + row] = pre_lse;
-      sDel[st * 128 + row] = pre_del;
+      if (hsel == 0) {
+        sLse[st * 128 + row] = pre_lse;
+        sDel[st * 128 + row] = pre_del;
+      }
       {
         const int qn = q0 + AB_T + row;                         // next tile's query handled by this thread
         const bool ok = (it + 1 < n_it) && qn < p.Sq;
         pre_lse = ok ? __ldg(LSE + qn) * 1.4426950408889634f : INFINITY;
         pre_del = ok ? __ldg(DEL + qn) : 0.f;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       mbar_wait(sdp_full, it & 1);
       tc_fence_after();
       const bool diag = p.causal && (q0 < k0 + AB_T);          // tile touches the causal boundary
 #pragma unroll 1
-      for (int qt = 0; qt < 4; ++qt) {                          // 32 query columns at a time (register budget)
+      for (int qt = 2 * hsel; qt < 2 * hsel + 2; ++qt) {        // this thread's 64 query columns, 32 at a time
         uint32_t s[32], dp[32];
         tmem_ld_32x32(tmem_base + AB_TM_S + lane_off + qt * 32, s);
         tmem_ld_32x32(tmem_base + AB_TM_DP + lane_off + qt * 32, dp);
         tmem_ld_wait();
-        if (qt == 3) {                                          // scores fully read: S^T / dP^T of the next tile may land
+        if (qt == 2 * hsel + 1) {                               // this thread's scores are read: S^T / dP^T of the next tile may land
           tc_fence_before();
           mbar_arrive(sdp_empty);
         }
@@ -269,7 +270,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           pk[q >> 1] = pack_bf16x2(pv[0], pv[1]);
           dk[q >> 1] = pack_bf16x2(dv[0], dv[1]);
         }
-        if (qt == 0) {                                          // P^T (TMEM) and dS^T (smem) of the previous tile consumed?
+        if (qt == 2 * hsel) {                                   // P^T (TMEM) and dS^T (smem) of the previous tile consumed?
           mbar_wait(pds_empty, (it & 1) ^ 1);                   // (waited for only now: the math above overlapped the MMAs)
           tc_fence_after();
         }
@@ -292,9 +293,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       tc_fence_after();
     }
     if (threadIdx.x == 0) tma_store_wait_read<0>();
-    named_bar_sync(2, 128);
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
+    named_bar_sync(2, 256);
+    {
+      const int which = hsel;                                   // warpgroup 0 drains dV_j, warpgroup 1 drains dK_j
       const uint32_t src = tmem_base + (which == 0 ? AB_TM_DV : AB_TM_DK) + lane_off;
       const uint32_t dst_row = sDQ_row + which * AB_TILE;
 #pragma unroll
@@ -316,7 +317,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       }
     }
     fence_proxy_async_smem();
-    named_bar_sync(3, 128);
+    named_bar_sync(3, 256);
     if (threadIdx.x == 0) {
       tma_store_3d_b(&tmap_dv, sDQ, h * AB_HD, k0, b);
       tma_store_3d_b(&tmap_dk, sDQ + AB_TILE, h * AB_HD, k0, b);
@@ -327,7 +328,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

@@ -11,8 +11,6 @@
 //
 // Replaces F.scaled_dot_product_attention (HF:integrations/sdpa_attention.py:40-104) for
 // HF:models/whisper/modeling_whisper.py:342-352 in the encoder (is_causal False), same contract as dwb_attention_fwd.
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace dwb {
@@ -226,10 +224,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         uint32_t pk[32];
 #pragma unroll
         for (int i = 0; i < 64; i += 2) {
-          const float a0 = fmaf(__uint_as_float(v[c * 64 + i]), p.scale_log2, -msc);
-          const float a1 = fmaf(__uint_as_float(v[c * 64 + i + 1]), p.scale_log2, -msc);
-          const float e0 = fast_exp2(a0);
-          const float e1 = ((i & 6) == 6) ? poly_exp2(a1) : fast_exp2(a1);   // 1 exponential in 8 on the FMA pipe
+          // (moving 1/8 of these to an FMA-pipe polynomial exp2 was measured: 0.572 vs 0.564 ms -- the MUFU pipe is not the limiter)
+          const float e0 = fast_exp2(fmaf(__uint_as_float(v[c * 64 + i]), p.scale_log2, -msc));
+          const float e1 = fast_exp2(fmaf(__uint_as_float(v[c * 64 + i + 1]), p.scale_log2, -msc));
           ls[(i >> 1) & 3] += e0 + e1;
           pk[i >> 1] = pack_bf16x2(e0, e1);
         }
@@ -271,228 +268,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   tc_fence_before();
   __syncthreads();
   if (warp == 5) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, TA_TMEM_COLS);
-  }
-}
-
-// =================================================================================================================
-// Variant with TWO softmax threads per query row (each owns 64 of the tile's 128 keys): 16 softmax warps per SM instead
-// of 8, so twice as many warps are available to cover each other's TMEM loads / barrier waits while the MUFU pipe (the
-// real bound at head_dim 64: 16 exp2/clk/SM) stays busy.  Row maxima are exchanged between the two threads of a row
-// through shared memory (one 64-thread named barrier per tile); row sums are combined once at the end.
-constexpr int TB_THREADS = 384;     // warps 0-3: keys [0,64) of each tile, warps 4-7: keys [64,128), warp 8 TMA, warp 9 MMA
-constexpr int TB_KV_STAGES = 2;
-constexpr int TB_TILES_BYTES = TA_TILE_BYTES + TB_KV_STAGES * 2 * TA_TILE_BYTES;
-constexpr int TB_XBUF_BYTES = 2 * 2 * 128 * 4;
-constexpr int TB_SMEM = 1024 + TB_TILES_BYTES + 128 + TB_XBUF_BYTES;
-
-__global__ void __launch_bounds__(TB_THREADS, 2)
-attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                    const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
-                    const TcAttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + TA_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + TB_KV_STAGES * 2 * TA_TILE_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;      // [2]
-  uint64_t* kv_empty = bars + 3;     // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* s_empty = bars + 6;
-  uint64_t* p_full = bars + 7;
-  uint64_t* p_empty = bars + 8;
-  uint64_t* o_full = bars + 9;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
-  float* xbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);   // [parity 2][half 2][row 128]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * TA_BQ;
-  const int b = blockIdx.y / p.H, h = blockIdx.y % p.H;
-  const int n_kv = ceil_div(p.Sk, TA_BK);
-
-  if (warp == 8 && lane == 0) {
-    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_o);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < TB_KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    mbar_init(s_full, 1); mbar_init(s_empty, 256);
-    mbar_init(p_full, 256); mbar_init(p_empty, 1);
-    mbar_init(o_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 9) {
-    tmem_alloc(tmem_ptr, TA_TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_s = tmem_base, tmem_p = tmem_base + 128, tmem_o = tmem_base + 192;
-
-  if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");      // 384 x 80 launch registers = 256 x 104 + 128 x 32
-  }
-  if (warp == 8) {
-    // ===================================== TMA producer (one thread) ========================
-    if (lane == 0) {
-      mbar_expect_tx(q_full, TA_TILE_BYTES);
-      tma_load_3d(&tmap_q, q_full, sQ, h * TA_HD, q0, b);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % TB_KV_STAGES;
-        mbar_wait(&kv_empty[st], ((j / TB_KV_STAGES) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[st], 2 * TA_TILE_BYTES);
-        tma_load_3d(&tmap_k, &kv_full[st], sKV + st * 2 * TA_TILE_BYTES, h * TA_HD, j * TA_BK, b);
-        tma_load_3d(&tmap_v, &kv_full[st], sKV + st * 2 * TA_TILE_BYTES + TA_TILE_BYTES, h * TA_HD, j * TA_BK, b);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 9) {
-    // ===================================== MMA issuer (one thread) ==========================
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
-      mbar_wait(q_full, 0);
-      const uint64_t dq = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-      auto issue_qk = [&](int j) {
-        const int st = j % TB_KV_STAGES;
-        mbar_wait(&kv_full[st], (j / TB_KV_STAGES) & 1);
-        mbar_wait(s_empty, (j & 1) ^ 1);
-        tc_fence_after();
-        const uint64_t dk = umma_desc_sw128(smem_u32(sKV + st * 2 * TA_TILE_BYTES), 16, 1024);
-#pragma unroll
-        for (int k = 0; k < TA_HD / 16; ++k) tc_mma_ss(tmem_s, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_qk, k > 0 ? 1u : 0u);
-        tc_commit(s_full);
-      };
-      issue_qk(0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % TB_KV_STAGES;
-        if (j + 1 < n_kv) issue_qk(j + 1);
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-        const uint64_t dv = umma_desc_sw128(smem_u32(sKV + st * 2 * TA_TILE_BYTES + TA_TILE_BYTES), TA_TILE_BYTES, 1024);
-#pragma unroll
-        for (int k = 0; k < TA_BK / 16; ++k)
-          tc_mma_ts(tmem_o, tmem_p + 8 * k, dv + (uint64_t)(k * 128), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-        tc_commit(o_full);
-        tc_commit(&kv_empty[st]);
-        tc_commit(p_empty);
-      }
-    }
-    __syncwarp();
-  } else if (warp < 8) {
-    // ===================================== softmax: two threads per query row ===============
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    const int wq = warp & 3, half = warp >> 2;
-    const int row = wq * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
-    const uint32_t t_s = tmem_s + lane_off + half * 64;
-    const uint32_t t_p = tmem_p + lane_off + half * 32;
-    const uint32_t t_o = tmem_o + lane_off + half * 32;
-    const int sw = row & 7;
-    float m_ref = -INFINITY, l_run = 0.f;
-
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      const int kbase = j * TA_BK + half * 64;
-      uint32_t v[64];
-      tmem_ld_32x32(t_s, v);
-      tmem_ld_32x32(t_s + 32, v + 32);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(s_empty);
-      if (kbase + 64 > p.Sk) {
-#pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (kbase + i >= p.Sk) v[i] = __float_as_uint(-INFINITY);
-      }
-      float mxp[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) mxp[c] = __uint_as_float(v[c]);
-#pragma unroll
-      for (int i = 8; i < 64; i += 8) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) mxp[c] = fmaxf(mxp[c], __uint_as_float(v[i + c]));
-      }
-      float mx = fmaxf(fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3])), fmaxf(fmaxf(mxp[4], mxp[5]), fmaxf(mxp[6], mxp[7])));
-      float* xb = xbuf + (j & 1) * 256;
-      xb[half * 128 + row] = mx;
-      named_bar_sync(1 + wq, 64);                            // the two warps that share these 32 rows
-      mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);            // full-row maximum (the other half may be all -inf: still finite here)
-      if (j == 0) {
-        m_ref = mx;
-      } else if ((mx - m_ref) * p.scale_log2 > 8.0f) {      // identical decision in both threads of the row
-        mbar_wait(o_full, (j - 1) & 1);
-        tc_fence_after();
-        const float f = fast_exp2((m_ref - mx) * p.scale_log2);
-        uint32_t o[32];
-        tmem_ld_32x32(t_o, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-        tmem_st_32x32(t_o, o);
-        tmem_st_wait();
-        tc_fence_before();
-        l_run *= f;
-        m_ref = mx;
-      }
-      const float msc = m_ref * p.scale_log2;
-      mbar_wait(p_empty, (j & 1) ^ 1);
-      tc_fence_after();
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {                          // 32 keys -> 16 packed columns per tcgen05.st
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float e0 = fast_exp2(fmaf(__uint_as_float(v[c * 32 + i]), p.scale_log2, -msc));
-          const float e1 = fast_exp2(fmaf(__uint_as_float(v[c * 32 + i + 1]), p.scale_log2, -msc));
-          ls[(i >> 1) & 3] += e0 + e1;
-          pk[i >> 1] = pack_bf16x2(e0, e1);
-        }
-        tmem_st_32x16(t_p + c * 16, pk);
-      }
-      tmem_st_wait();
-      l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-      tc_fence_before();
-      mbar_arrive(p_full);
-    }
-    // epilogue: combine the two partial row sums, normalise this thread's 32 output columns
-    mbar_wait(o_full, (n_kv - 1) & 1);
-    tc_fence_after();
-    float* xb = xbuf + (n_kv & 1) * 256;                     // the parity not used by the last tile's exchange
-    xb[half * 128 + row] = l_run;
-    named_bar_sync(1 + wq, 64);
-    const float l_tot = l_run + xb[(half ^ 1) * 128 + row];
-    const float inv = 1.f / l_tot;
-    const uint32_t sO_row = smem_u32(sQ) + row * 128;
-    {
-      uint32_t o[32];
-      tmem_ld_32x32(t_o, o);
-      tmem_ld_wait();
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        const float* f = reinterpret_cast<const float*>(o) + ch * 8;
-        st_shared_v4(sO_row + (((half * 4 + ch) ^ sw) << 4), pack_bf16x2(f[0] * inv, f[1] * inv), pack_bf16x2(f[2] * inv, f[3] * inv),
-                     pack_bf16x2(f[4] * inv, f[5] * inv), pack_bf16x2(f[6] * inv, f[7] * inv));
-      }
-    }
-    fence_proxy_async_smem();
-    named_bar_sync(5, 256);
-    if (threadIdx.x == 0) {
-      tma_store_3d(&tmap_o, sQ, h * TA_HD, q0, b);
-      tma_store_commit();
-      tma_store_wait_all<0>();
-    }
-    if (half == 0 && p.lse != nullptr && q0 + row < p.Sq)
-      p.lse[((int64_t)b * p.H + h) * p.Sq + q0 + row] = m_ref * p.scale + __logf(l_tot);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TA_TMEM_COLS);
   }
@@ -544,24 +319,10 @@ extern "C" int dwb_attention_fwd_tc(const void* q, int64_t ldq, const void* k, i
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse;
   dim3 grid(ceil_div(Sq, TA_BQ), B * H);
-  static int variant = -1;
-  if (variant < 0) {
-    // 1 (default): one softmax thread per row -- 0.60 ms per encoder layer at B=32 on B200.
-    // 2: two threads per row -- measured slower (0.70 ms: the pair barrier + half-size TMEM accesses cost more than the extra
-    //    warps hide); kept selectable for the round-2 attention work.
-    const char* e = getenv("DWB_ATTN_VARIANT");
-    variant = (e && e[0] == '2') ? 2 : 1;
-  }
-  if (variant == 2) {
-    static bool attr2 = false;
-    if (!attr2) {
-      DWB_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM));
-      attr2 = true;
-    }
-    attn_fwd_tc2_kernel<<<grid, TB_THREADS, TB_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, to, p);
-  } else {
-    attn_fwd_tc_kernel<<<grid, TA_THREADS, TA_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, to, p);
-  }
+  // (A variant with two softmax threads per query row -- 16 softmax warps per SM -- was built and measured in round 1:
+  //  0.70 ms vs 0.60 ms per encoder layer, i.e. slower: the pair barrier and half-width TMEM accesses cost more than the
+  //  extra warps hide.  See profiles/README.md.)
+  attn_fwd_tc_kernel<<<grid, TA_THREADS, TA_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, to, p);
   DWB_LAUNCH_OK();
   return DWB_OK;
 }

@@ -268,19 +268,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 2^x for x <= 0 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax
-// polynomial for 2^f (max rel. error 1.0e-4, below the bf16 rounding of the probabilities it feeds), exponent added with
-// an integer shift of the magic-number sum.  Used for a fraction of the softmax exponentials so that the 16-op/clk MUFU
-// pipe is not the only unit working during the exp phase.
-__device__ __forceinline__ float poly_exp2(float x) {
-  x = fmaxf(x, -125.0f);
-  const float t = x + 12582912.0f;                 // 1.5 * 2^23: the low mantissa bits of t now hold round(x)
-  const float f = x - (t - 12582912.0f);
-  float p = fmaf(0.05592203512787819f, f, 0.24264007806777954f);
-  p = fmaf(p, f, 0.6931210160255432f);
-  p = fmaf(p, f, 0.9999244809150696f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
