@@ -274,6 +274,260 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs (the two SMs of a TPC) computes a 256 x 256 tile with one
+// 256-row tcgen05.mma per K step.  Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256
+// columns); the tensor cores of both SMs read the two B halves from both shared memories.  Per SM and K block that is
+// 32 KB of TMA writes and operand reads instead of 48 KB, and the ring holds 6 stages instead of 4.
+//   * both producers' TMA bytes are accounted on the LEADER's (cluster rank 0) full barrier; only the leader issues MMAs;
+//   * tcgen05.commit multicasts "stage free" / "accumulator ready" to the barriers at the same offset in both CTAs;
+//   * the peer's epilogue warps release the accumulator with a remote mbarrier arrive on the leader.
+struct Gemm2Cfg {
+  static constexpr int BN = 256, BNH = 128;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BNH * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (192 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kUsedBytes = kStages * kStageBytes + 2 * kPanelBytes + 256 + 2 * BN * 4;
+  static constexpr int kSmemBytes = 512 + kUsedBytes;
+};
+static_assert(2 * Gemm2Cfg::kStages + 4 <= 31, "barriers + TMEM pointer must fit in the 256 B in front of the bias slices");
+
+template <int A_MN, int B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+  using Cfg = Gemm2Cfg;
+  constexpr int BN = Cfg::BN, BNH = Cfg::BNH;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (threadIdx.x == 0 && (int)(smem - smem_raw) + Cfg::kUsedBytes > Cfg::kSmemBytes) {
+    printf("dwb: gemm smem window misaligned by %d B\n", (int)(smem - smem_raw));
+    __trap();
+  }
+  uint8_t* panels = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(panels + 2 * kPanelBytes);
+  uint64_t* full_bar = bars;                      // [kStages]   (only the leader's are waited on)
+  uint64_t* empty_bar = bars + Cfg::kStages;      // [kStages]
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]        (only the leader's are waited on)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(bars) + 64;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  const int m_tiles = ceil_div(p.M, 2 * BM);
+  const int n_tiles = ceil_div(p.N, BN);
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb_total = ceil_div(p.K, BK);
+  const int kb_per_split = ceil_div(num_kb_total, p.split_k);
+  const int num_items = num_tiles * p.split_k;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_c);
+  }
+  if (warp == 5 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);               // one arrive per epilogue warp of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc_2cta(tmem_ptr, Cfg::kTmemCols);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();                             // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 4) {
+    // ===================================== TMA producer (both CTAs) ==========================
+    const bool leader = elect_one();
+    const uint32_t full0 = mapa_u32(smem_u32(&full_bar[0]), 0);   // the pair leader's full barriers
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = cluster_id; item < num_items; item += num_clusters) {
+      const int tile = item % num_tiles;
+      const int split = item / num_tiles;
+      const int m0 = (tile / n_tiles) * (2 * BM) + (int)rank * BM;
+      const int n0 = (tile % n_tiles) * BN + (int)rank * BNH;     // this CTA's half of the B tile
+      const int kb0 = split * kb_per_split;
+      const int kb1 = min(kb0 + kb_per_split, num_kb_total);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) {
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          const uint32_t fb = full0 + stage * 8;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);   // both CTAs' bytes land on this barrier
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(&tmap_a, fb, sa + j * (BK * 128), m0 + 64 * j, kb * BK);
+          } else {
+            tma_load_2d_2sm(&tmap_a, fb, sa, kb * BK, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BNH / 64; ++j) tma_load_2d_2sm(&tmap_b, fb, sb + j * (BK * 128), n0 + 64 * j, kb * BK);
+          } else {
+            tma_load_2d_2sm(&tmap_b, fb, sb, kb * BK, n0);
+          }
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ===================================== MMA issuer (leader CTA only) ======================
+    if (rank == 0) {
+      const bool leader = elect_one();
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, A_MN, B_MN);
+      constexpr uint32_t a_kstep = A_MN ? (2 * 1024) >> 4 : 32 >> 4;
+      constexpr uint32_t b_kstep = B_MN ? (2 * 1024) >> 4 : 32 >> 4;
+      constexpr uint32_t a_lbo = A_MN ? BK * 128 : 16;
+      constexpr uint32_t b_lbo = B_MN ? BK * 128 : 16;
+      const uint64_t da0 = umma_desc_sw128(smem_u32(smem), a_lbo, 1024);
+      const uint64_t db0 = umma_desc_sw128(smem_u32(smem) + Cfg::kABytes, b_lbo, 1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local_it = 0;
+      for (int item = cluster_id; item < num_items; item += num_clusters, ++local_it) {
+        const int split = item / num_tiles;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, num_kb_total);
+        const int acc = local_it & 1;
+        const uint32_t acc_phase = (local_it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (leader) {
+            const uint64_t da = da0 + (uint64_t)(stage * (Cfg::kStageBytes >> 4));
+            const uint64_t db = db0 + (uint64_t)(stage * (Cfg::kStageBytes >> 4));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              tc_mma_ss_2cta(tmem_d, da + (uint64_t)(k * a_kstep), db + (uint64_t)(k * b_kstep), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit_2cta(&empty_bar[stage], 3);             // frees the stage in both CTAs
+            if (kb == kb1 - 1) tc_commit_2cta(&tmem_full[acc], 3);
+          }
+          __syncwarp();
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        if (kb1 <= kb0 && leader) tc_commit_2cta(&tmem_full[acc], 3);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================== epilogue (warps 0-3 of both CTAs) ==================
+    const int q = warp;
+    const int epi_tid = threadIdx.x;
+    const int panel_cols = p.c_f32 ? 32 : 64;
+    const int panels_per_tile = BN / panel_cols;
+    uint8_t* my_panels = panels + q * (2 * kWarpPanelBytes);
+    const uint32_t row_saddr = smem_u32(my_panels) + lane * 128;
+    const int sw = lane & 7;
+    const uint32_t tmem_empty0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);   // the leader's accumulator-free barriers
+    int local_it = 0;
+    int panel_it = 0;
+    for (int item = cluster_id; item < num_items; item += num_clusters, ++local_it) {
+      const int tile = item % num_tiles;
+      const int m0 = (tile / n_tiles) * (2 * BM) + (int)rank * BM + q * 32;
+      const int n0 = (tile % n_tiles) * BN;
+      const int acc = local_it & 1;
+      const uint32_t acc_phase = (local_it >> 1) & 1;
+      float* sb = s_bias + (local_it & 1) * BN;
+      for (int c = epi_tid; c < BN; c += kEpiThreads) sb[c] = (p.bias != nullptr && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
+      named_bar_sync(1, kEpiThreads);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      bool released = false;
+      for (int pi = 0; pi < panels_per_tile; ++pi, ++panel_it) {
+        const int c0 = pi * panel_cols;
+        if (n0 + c0 >= p.N) break;
+        uint32_t v[64];
+        tmem_ld_32x32(t_row + c0, v);
+        if (!p.c_f32) tmem_ld_32x32(t_row + c0 + 32, v + 32);
+        tmem_ld_wait();
+        const bool last_panel = (pi == panels_per_tile - 1) || (n0 + c0 + panel_cols >= p.N);
+        if (last_panel) {                         // accumulator fully read by this warp: tell the leader's MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tmem_empty0 + acc * 8);
+          released = true;
+        }
+        const uint32_t buf_off = (panel_it & 1) * kWarpPanelBytes;
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        const float4* sb4 = reinterpret_cast<const float4*>(sb + c0);
+        if (p.c_f32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = sb4[j];
+            float f0 = fmaf(__uint_as_float(v[j * 4 + 0]), p.alpha, bb.x), f1 = fmaf(__uint_as_float(v[j * 4 + 1]), p.alpha, bb.y);
+            float f2 = fmaf(__uint_as_float(v[j * 4 + 2]), p.alpha, bb.z), f3 = fmaf(__uint_as_float(v[j * 4 + 3]), p.alpha, bb.w);
+            if (p.act == 1) { f0 = gelu_erf_fast(f0); f1 = gelu_erf_fast(f1); f2 = gelu_erf_fast(f2); f3 = gelu_erf_fast(f3); }
+            st_shared_v4(row_saddr + buf_off + ((j ^ sw) << 4), __float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2),
+                         __float_as_uint(f3));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b0 = sb4[2 * j], b1 = sb4[2 * j + 1];
+            float f[8];
+            f[0] = fmaf(__uint_as_float(v[j * 8 + 0]), p.alpha, b0.x); f[1] = fmaf(__uint_as_float(v[j * 8 + 1]), p.alpha, b0.y);
+            f[2] = fmaf(__uint_as_float(v[j * 8 + 2]), p.alpha, b0.z); f[3] = fmaf(__uint_as_float(v[j * 8 + 3]), p.alpha, b0.w);
+            f[4] = fmaf(__uint_as_float(v[j * 8 + 4]), p.alpha, b1.x); f[5] = fmaf(__uint_as_float(v[j * 8 + 5]), p.alpha, b1.y);
+            f[6] = fmaf(__uint_as_float(v[j * 8 + 6]), p.alpha, b1.z); f[7] = fmaf(__uint_as_float(v[j * 8 + 7]), p.alpha, b1.w);
+            if (p.act == 1) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = gelu_erf_fast(f[e]);
+            }
+            st_shared_v4(row_saddr + buf_off + ((j ^ sw) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                         pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.reduce_add) tma_reduce_add_2d(&tmap_c, my_panels + buf_off, n0 + c0, m0);
+          else tma_store_2d(&tmap_c, my_panels + buf_off, n0 + c0, m0);
+          tma_store_commit();
+        }
+      }
+      if (!released) {                            // (cannot happen: n0 < N for every scheduled tile) keep the protocol whole
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tmem_empty0 + acc * 8);
+      }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                             // both CTAs are done with both TMEMs / shared memories
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // plain SIMT GEMM with the same contract: debugging aid and on-device cross-check for the tests.
 __global__ void gemm_bf16_simt_kernel(const bf16* __restrict__ A, int64_t lda, int a_mn, const bf16* __restrict__ B,
                                       int64_t ldb, int b_mn, void* __restrict__ C, int64_t ldc, int c_f32, int M, int N,
@@ -358,6 +612,30 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   return DWB_OK;
 }
 
+template <int A_MN, int B_MN>
+static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int items,
+                            cudaStream_t st) {
+  auto kern = gemm_bf16_2cta_kernel<A_MN, B_MN>;
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    DWB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::kSmemBytes));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * kNumSMs);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Gemm2Cfg::kSmemBytes;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = kNumSMs / 2;
+    }
+    max_clusters = n;
+  }
+  const int clusters = items < max_clusters ? items : max_clusters;
+  kern<<<2 * clusters, kGemmThreads, Gemm2Cfg::kSmemBytes, st>>>(ta, tb, tc, p);
+  DWB_LAUNCH_OK();
+  return DWB_OK;
+}
+
 static int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -389,7 +667,7 @@ extern "C" int dwb_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const v
     DWB_LAUNCH_OK();
     return DWB_OK;
   }
-  DWB_CHECK_ARG(impl == 0, "dwb_gemm_bf16: unknown impl %d", impl);
+  DWB_CHECK_ARG(impl == 0 || impl == 2 || impl == 3, "dwb_gemm_bf16: unknown impl %d (0 auto, 1 SIMT, 2 CTA pair, 3 single CTA)", impl);
 
   // tile shape / split-K heuristic: fill 148 SMs in as few full waves as possible
   const int sms = num_sms();
@@ -402,7 +680,17 @@ extern "C" int dwb_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const v
     const double w256 = (double)ceil_div(t256, sms) * 1.0, w128 = (double)ceil_div(t128, sms) * 0.8;
     if (N <= 128 || w128 < w256) bn = 128;
   }
-  const int tiles = m_tiles * ceil_div(N, bn);
+  // CTA pairs (256 x 256 tiles, 74 clusters): worth it when the problem fills the pairs for several rounds
+  static const int pair_env = [] { const char* e = getenv("DWB_GEMM_2CTA"); return e ? atoi(e) : 1; }();
+  bool pair = false;
+  if (impl == 2) pair = true;
+  else if (impl == 0 && pair_env && bn == 256 && N >= 256) {
+    const int t2 = ceil_div(M, 2 * BM) * ceil_div(N, 256), clusters = sms / 2;
+    const int rounds2 = ceil_div(t2, clusters), rounds1 = ceil_div(m_tiles * ceil_div(N, 256), sms);
+    pair = t2 >= 4 * clusters && rounds2 <= rounds1 + (rounds1 >= 16 ? 1 : 0);
+  }
+  if (pair) bn = 256;
+  const int tiles = pair ? ceil_div(M, 2 * BM) * ceil_div(N, 256) : m_tiles * ceil_div(N, bn);
   const int num_kb = ceil_div(K, BK);
   int split_k = 1;
   if (c_f32 && bias == nullptr && act == 0 && tiles * 2 <= sms && num_kb >= 16) {
@@ -430,12 +718,20 @@ extern "C" int dwb_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const v
   else rc = make_tmap_2d(&ta, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
   if (rc) return rc;
   if (b_mn_major) rc = make_tmap_2d(&tb, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, 64);
-  else rc = make_tmap_2d(&tb, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)bn, BK);
+  else rc = make_tmap_2d(&tb, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)(pair ? 128 : bn), BK);
   if (rc) return rc;
   rc = make_tmap_2d(&tc, C, c_f32 ? 4 : 2, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, c_f32 ? 32 : 64);   // one epilogue warp's slab
   if (rc) return rc;
 
   const int items = tiles * split_k;
+  if (pair) {
+    switch ((a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0)) {
+      case 0: return launch_gemm_2cta<0, 0>(ta, tb, tc, p, items, st);
+      case 1: return launch_gemm_2cta<0, 1>(ta, tb, tc, p, items, st);
+      case 2: return launch_gemm_2cta<1, 0>(ta, tb, tc, p, items, st);
+      default: return launch_gemm_2cta<1, 1>(ta, tb, tc, p, items, st);
+    }
+  }
   const int grid = items < sms ? items : sms;
   const int key = (bn == 256 ? 4 : 0) | (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
   switch (key) {

@@ -39,11 +39,14 @@ def bench_gemm():
         ld = ops.round_up(N, 8)
         c = torch.empty((M, ld), device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)[:, :N]
         ms = timeit(lambda: ops.gemm(a, b, a_mn=bool(amn), b_mn=bool(bmn), bias=bias, act=act, out=c))
+        ms1 = timeit(lambda: ops.gemm(a, b, a_mn=bool(amn), b_mn=bool(bmn), bias=bias, act=act, out=c, impl=3))
+        ms2 = timeit(lambda: ops.gemm(a, b, a_mn=bool(amn), b_mn=bool(bmn), bias=bias, act=act, out=c, impl=2)) if N >= 256 else float("nan")
         aT = a.t() if amn else a
         bT = b if bmn else b.t()
         ms_t = timeit(lambda: torch.matmul(aT, bT))
         tf = 2.0 * M * N * K / ms / 1e9
         out.append(dict(M=M, N=N, K=K, a_mn=amn, b_mn=bmn, act=act, f32=f32, ms=round(ms, 4), tflops=round(tf, 1),
+                        single_cta_tflops=round(2.0 * M * N * K / ms1 / 1e9, 1), cta_pair_tflops=round(2.0 * M * N * K / ms2 / 1e9, 1),
                         cublas_ms=round(ms_t, 4), cublas_tflops=round(2.0 * M * N * K / ms_t / 1e9, 1)))
         print(out[-1], flush=True)
     return out

@@ -86,3 +86,35 @@ def test_gemm_rejects_misaligned_pitch(ops):
     a, b = _mk((64, 68), 9), _mk((64, 68), 10)      # pitch 68 * 2 B = 136 B: not a multiple of 16 B
     with pytest.raises(DwbError):
         ops.gemm(a[:, :64], b[:, :64])
+
+
+PAIR_SHAPES = [(256, 256, 64), (512, 512, 320), (304, 136, 240), (1000, 520, 1280), (4096, 1280, 1280), (72, 1288, 200), (2000, 3840, 384)]
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", PAIR_SHAPES)
+def test_gemm_cta_pair_layouts(ops, M, N, K, a_mn, b_mn):
+    """cta_group::2 kernel forced (impl=2): 256-row MMAs issued by the pair leader, B tile split across the two CTAs;
+    covers M/N tails (a peer CTA whose 128 rows are entirely out of range) and many rounds per cluster."""
+    a = _mk((K, M) if a_mn else (M, K), 11, 0.5)
+    b = _mk((K, N) if b_mn else (N, K), 12, 0.5)
+    bias = torch.randn(N, device="cuda")
+    out = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, bias=bias, act=0, impl=2)
+    ref = _ref(a, b, a_mn, b_mn, bias, 0, 1.0)
+    assert _rel(out, ref) < 6e-3, _rel(out, ref)
+    single = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, bias=bias, act=0, impl=3)
+    assert torch.equal(out, single)          # same K order, same epilogue: bit-identical to the single-CTA kernel
+
+
+def test_gemm_cta_pair_gelu_and_f32_accumulate(ops):
+    M, N, K = 1500, 5120, 1280
+    a, b = _mk((M, K), 13, 0.3), _mk((N, K), 14, 0.3)
+    bias = torch.randn(N, device="cuda") * 0.1
+    out = ops.gemm(a, b, bias=bias, act=1, impl=2)
+    assert _rel(out, _ref(a, b, False, False, bias, 1, 1.0)) < 8e-3
+    M, N, K = 1280, 1288, 4096
+    a, b = _mk((K, M), 15, 0.2), _mk((K, N), 16, 0.2)
+    base = torch.randn(M, N, device="cuda")
+    acc = base.clone()
+    ops.gemm(a, b, a_mn=True, b_mn=True, out=acc, alpha=0.5, accumulate=True, impl=2)
+    assert _rel(acc, base + _ref(a, b, True, True, None, 0, 0.5)) < 2e-5
