@@ -23,7 +23,7 @@ constexpr int TA_TILES_BYTES = TA_TILE_BYTES /*Q, reused for the output tile*/ +
 constexpr int TA_BAR_BYTES = 112;
 // two CTAs per SM: 2 * (dyn + 1 KB system reserve) <= 228 KB  ->  dyn <= 115712; the slack absorbs the 1 KB round-up
 constexpr int TA_SMEM = 115712;
-static_assert(TA_TILES_BYTES + TA_BAR_BYTES + 512 <= TA_SMEM, "smem budget");
+static_assert(TA_TILES_BYTES + TA_BAR_BYTES + 896 <= TA_SMEM, "smem budget");
 constexpr int TA_TMEM_COLS = 256;
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2) {
@@ -273,267 +273,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// Variant with EIGHT softmax warps (two threads per query row, 64 keys each).  A warp-wide MUFU.EX2 holds the issuing
-// warp for ~8 cycles (4 XU lanes per SM sub-partition), so with one softmax warp per CTA per sub-partition the XU pipe
-// idles whenever that warp is loading scores, reducing the maximum or storing P (ncu: XU 63 % busy, exp2 loop = 55 % of
-// a softmax warp's samples).  Four softmax warps per sub-partition (2 CTAs x 2) keep the XU fed.
-// No per-tile exchange between the two threads of a row: each reduces the maximum over the FULL row (it reads the
-// partner's 64 scores from TMEM as well -- TMEM read bandwidth is cheap, a pair barrier per tile is not), so both take
-// identical rescale decisions; only the row sums are combined, once, at the end.
-constexpr int TA8_THREADS = 384;  // warps 0-7 softmax (warp & 3 = TMEM lane quadrant, warp >> 2 = key half), 8 TMA, 9 MMA,
-                                  // 10-11 idle: setmaxnreg is warpgroup-aligned, the third warpgroup must be complete
-
-__device__ __forceinline__ float max32(const uint32_t* u) {
-  float a = fmaxf(__uint_as_float(u[0]), __uint_as_float(u[1])), b2 = fmaxf(__uint_as_float(u[2]), __uint_as_float(u[3]));
-  float c = fmaxf(__uint_as_float(u[4]), __uint_as_float(u[5])), d = fmaxf(__uint_as_float(u[6]), __uint_as_float(u[7]));
-#pragma unroll
-  for (int i = 8; i < 32; i += 8) {
-    a = fmaxf(a, fmaxf(__uint_as_float(u[i]), __uint_as_float(u[i + 1])));
-    b2 = fmaxf(b2, fmaxf(__uint_as_float(u[i + 2]), __uint_as_float(u[i + 3])));
-    c = fmaxf(c, fmaxf(__uint_as_float(u[i + 4]), __uint_as_float(u[i + 5])));
-    d = fmaxf(d, fmaxf(__uint_as_float(u[i + 6]), __uint_as_float(u[i + 7])));
-  }
-  return fmaxf(fmaxf(a, b2), fmaxf(c, d));
-}
-
-__global__ void __launch_bounds__(TA8_THREADS, 2)
-attn_fwd_tc8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                    const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
-                    const TcAttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  if (threadIdx.x == 0 && (smem - smem_raw) + TA_TILES_BYTES + TA_BAR_BYTES + 512 > TA_SMEM) {
-    printf("dwb: attention smem window misaligned by %d B\n", (int)(smem - smem_raw));
-    __trap();
-  }
-  uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + TA_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + TA_KV_STAGES * 2 * TA_TILE_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = bars + 4;
-  uint64_t* s_full = bars + 7;
-  uint64_t* s_empty = bars + 8;
-  uint64_t* p_full = bars + 9;
-  uint64_t* p_empty = bars + 10;
-  uint64_t* o_full = bars + 11;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
-  float* l_x = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + TA_BAR_BYTES);   // [128] row-sum exchange
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * TA_BQ;
-  const int b = blockIdx.y / p.H, h = blockIdx.y % p.H;
-  const int n_kv = ceil_div(p.causal ? min(p.Sk, q0 + TA_BQ) : p.Sk, TA_BK);
-
-  if (warp == 8 && lane == 0) {
-    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_o);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < TA_KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    mbar_init(s_full, 1); mbar_init(s_empty, 256);
-    mbar_init(p_full, 256); mbar_init(p_empty, 1);
-    mbar_init(o_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 9) {
-    tmem_alloc(tmem_ptr, TA_TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_s = tmem_base;
-  const uint32_t tmem_p = tmem_base + 128;
-  const uint32_t tmem_o = tmem_base + 192;
-
-  // launch: 80 registers/thread (2 CTAs x 384 threads); the softmax warpgroups take 104, the third warpgroup keeps 32
-  if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-  }
-  if (warp == 8) {
-    const bool leader = elect_one();
-    if (leader) {
-      mbar_expect_tx(q_full, TA_TILE_BYTES);
-      tma_load_3d(&tmap_q, q_full, sQ, h * TA_HD, q0, b);
-    }
-    for (int j = 0; j < n_kv; ++j) {
-      const int st = j % TA_KV_STAGES;
-      mbar_wait(&kv_empty[st], ((j / TA_KV_STAGES) & 1) ^ 1);
-      if (leader) {
-        mbar_expect_tx(&kv_full[st], 2 * TA_TILE_BYTES);
-        tma_load_3d(&tmap_k, &kv_full[st], sKV + st * 2 * TA_TILE_BYTES, h * TA_HD, j * TA_BK, b);
-        tma_load_3d(&tmap_v, &kv_full[st], sKV + st * 2 * TA_TILE_BYTES + TA_TILE_BYTES, h * TA_HD, j * TA_BK, b);
-      }
-      __syncwarp();
-    }
-  } else if (warp == 9) {
-    const bool leader = elect_one();
-    constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
-    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
-    mbar_wait(q_full, 0);
-    const uint64_t dq = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-    auto issue_qk = [&](int j) {
-      const int st = j % TA_KV_STAGES;
-      mbar_wait(&kv_full[st], (j / TA_KV_STAGES) & 1);
-      mbar_wait(s_empty, (j & 1) ^ 1);
-      tc_fence_after();
-      if (leader) {
-        const uint64_t dk = umma_desc_sw128(smem_u32(sKV + st * 2 * TA_TILE_BYTES), 16, 1024);
-#pragma unroll
-        for (int k = 0; k < TA_HD / 16; ++k) tc_mma_ss(tmem_s, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_qk, k > 0 ? 1u : 0u);
-        tc_commit(s_full);
-      }
-      __syncwarp();
-    };
-    issue_qk(0);
-    for (int j = 0; j < n_kv; ++j) {
-      const int st = j % TA_KV_STAGES;
-      if (j + 1 < n_kv) issue_qk(j + 1);
-      mbar_wait(p_full, j & 1);
-      tc_fence_after();
-      if (leader) {
-        const uint64_t dv = umma_desc_sw128(smem_u32(sKV + st * 2 * TA_TILE_BYTES + TA_TILE_BYTES), TA_TILE_BYTES, 1024);
-#pragma unroll
-        for (int k = 0; k < TA_BK / 16; ++k)
-          tc_mma_ts(tmem_o, tmem_p + 8 * k, dv + (uint64_t)(k * 128), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-        tc_commit(o_full);
-        tc_commit(&kv_empty[st]);
-        tc_commit(p_empty);
-      }
-      __syncwarp();
-    }
-  } else if (warp < 8) {
-    // ===================================== softmax / output: two threads per query row ======================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    const int quad = warp & 3, half = warp >> 2;
-    const int row = quad * 32 + lane;                       // query row == TMEM lane
-    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    const uint32_t t_s = tmem_s + lane_off;
-    const uint32_t t_o = tmem_o + lane_off + 32 * half;     // this thread's 32 of the 64 output columns
-    const uint32_t t_p = tmem_p + lane_off + 32 * half;     // 64 keys -> 32 packed columns
-    const int my_c = 64 * half, ot_c = 64 * (half ^ 1);
-    const int sw = row & 7;
-    float m_ref = -INFINITY, l_run = 0.f;
-
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      const int kbase = j * TA_BK;
-      const bool tail = kbase + TA_BK > p.Sk;
-      const bool diag = p.causal && (kbase + TA_BK - 1 > q0);
-      const bool masked = tail || diag;
-      const int lim = diag ? min(p.Sk, q0 + row + 1) : p.Sk;   // first masked key index for this query row
-      float mx;
-      {
-        uint32_t u[64];                                     // the partner's 64 scores: only their maximum is needed
-        tmem_ld_32x32(t_s + ot_c, u);
-        tmem_ld_32x32(t_s + ot_c + 32, u + 32);
-        tmem_ld_wait();
-        if (masked) {
-#pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if (kbase + ot_c + i >= lim) u[i] = __float_as_uint(-INFINITY);
-        }
-        mx = fmaxf(max32(u), max32(u + 32));
-      }
-      uint32_t v[64];
-      tmem_ld_32x32(t_s + my_c, v);
-      tmem_ld_32x32(t_s + my_c + 32, v + 32);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(s_empty);                                 // scores are in registers: QK^T of the next tile may start
-      if (masked) {
-#pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (kbase + my_c + i >= lim) v[i] = __float_as_uint(-INFINITY);
-      }
-      mx = fmaxf(mx, fmaxf(max32(v), max32(v + 32)));
-      if (j == 0) {
-        m_ref = mx;
-      } else if ((mx - m_ref) * p.scale_log2 > 8.0f) {
-        // rare, and taken by both threads of the row (identical mx): bring O (TMEM) and l to the new reference maximum
-        mbar_wait(o_full, (j - 1) & 1);
-        tc_fence_after();
-        const float f = fast_exp2((m_ref - mx) * p.scale_log2);
-        uint32_t o[32];
-        tmem_ld_32x32(t_o, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-        tmem_st_32x32(t_o, o);
-        tmem_st_wait();
-        tc_fence_before();
-        l_run *= f;
-        m_ref = mx;
-      }
-      const float msc = m_ref * p.scale_log2;
-      mbar_wait(p_empty, (j & 1) ^ 1);                      // P V of the previous tile has consumed P
-      tc_fence_after();
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {                         // 32 keys -> 16 packed columns per tcgen05.st
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float e0 = fast_exp2(fmaf(__uint_as_float(v[c * 32 + i]), p.scale_log2, -msc));
-          const float e1 = fast_exp2(fmaf(__uint_as_float(v[c * 32 + i + 1]), p.scale_log2, -msc));
-          ls[(i >> 1) & 3] += e0 + e1;
-          pk[i >> 1] = pack_bf16x2(e0, e1);
-        }
-        tmem_st_32x16(t_p + c * 16, pk);
-      }
-      tmem_st_wait();
-      l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-      tc_fence_before();
-      mbar_arrive(p_full);
-    }
-    // row sum = sum of the two halves (both threads need it: each normalises its own 32 output columns)
-    auto pair_sync = [&]() {                                // the two warps of a lane quadrant (constant ids: ptxas reserves only these)
-      if (quad == 0) named_bar_sync(2, 64);
-      else if (quad == 1) named_bar_sync(3, 64);
-      else if (quad == 2) named_bar_sync(4, 64);
-      else named_bar_sync(5, 64);
-    };
-    if (half == 1) l_x[row] = l_run;
-    pair_sync();
-    if (half == 0) { l_run += l_x[row]; l_x[row] = l_run; }
-    pair_sync();
-    if (half == 1) l_run = l_x[row];
-    mbar_wait(o_full, (n_kv - 1) & 1);
-    tc_fence_after();
-    const float inv = 1.f / l_run;
-    const uint32_t sO_row = smem_u32(sQ) + row * 128;
-    {
-      uint32_t o[32];
-      tmem_ld_32x32(t_o, o);
-      tmem_ld_wait();
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        const float* f = reinterpret_cast<const float*>(o) + ch * 8;
-        st_shared_v4(sO_row + (((half * 4 + ch) ^ sw) << 4), pack_bf16x2(f[0] * inv, f[1] * inv), pack_bf16x2(f[2] * inv, f[3] * inv),
-                     pack_bf16x2(f[4] * inv, f[5] * inv), pack_bf16x2(f[6] * inv, f[7] * inv));
-      }
-    }
-    fence_proxy_async_smem();
-    named_bar_sync(1, 256);
-    if (threadIdx.x == 0) {
-      tma_store_3d(&tmap_o, sQ, h * TA_HD, q0, b);
-      tma_store_commit();
-      tma_store_wait_all<0>();
-    }
-    if (half == 0 && p.lse != nullptr && q0 + row < p.Sq)
-      p.lse[((int64_t)b * p.H + h) * p.Sq + q0 + row] = m_ref * p.scale + __logf(l_run);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, TA_TMEM_COLS);
-  }
-}
-
 // [B, S, cols] view of a [B*S, ld] matrix as a 3-D tensor map; box = 64 columns x 128 rows x 1 batch, 128B swizzle
 static int make_tmap_bsc(CUtensorMap* out, const void* base, int64_t ld, int B, int S, int cols) {
   PFN_encodeTiled enc = get_encode_tiled();
@@ -572,7 +311,6 @@ extern "C" int dwb_attention_fwd_tc(const void* q, int64_t ldq, const void* k, i
   static bool attr = false;
   if (!attr) {
     DWB_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
-    DWB_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
     attr = true;
   }
   TcAttnParams p;
@@ -581,14 +319,11 @@ extern "C" int dwb_attention_fwd_tc(const void* q, int64_t ldq, const void* k, i
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse;
   dim3 grid(ceil_div(Sq, TA_BQ), B * H);
-  // (A variant with two softmax threads per query row -- 16 softmax warps per SM -- was built and measured in round 1:
-  //  0.70 ms vs 0.60 ms per encoder layer, i.e. slower: the pair barrier and half-width TMEM accesses cost more than the
-  //  extra warps hide.  See profiles/README.md.)
-  static const int impl8 = [] { const char* e = getenv("DWB_ATTN_FWD_WARPS"); return (e && atoi(e) == 4) ? 0 : 1; }();
-  if (impl8)
-    attn_fwd_tc8_kernel<<<grid, TA8_THREADS, TA_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, to, p);
-  else
-    attn_fwd_tc_kernel<<<grid, TA_THREADS, TA_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, to, p);
+  // (Two variants with two softmax threads per query row -- 16 softmax warps per SM -- were built and measured in round 1:
+  //  with a per-tile pair barrier 0.70 ms, with each thread reducing the full-row maximum itself (no exchange) 0.62 ms,
+  //  against 0.56 ms for this kernel: the XU pipe is busy 63 % of the time here, but the extra TMEM traffic and the
+  //  tighter register budget (104/thread) cost more than the additional warps recover.  See profiles/README.md.)
+  attn_fwd_tc_kernel<<<grid, TA_THREADS, TA_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, to, p);
   DWB_LAUNCH_OK();
   return DWB_OK;
 }

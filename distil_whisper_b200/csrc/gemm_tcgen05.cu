@@ -687,7 +687,9 @@ extern "C" int dwb_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const v
   else if (impl == 0 && pair_env && bn == 256 && N >= 256) {
     const int t2 = ceil_div(M, 2 * BM) * ceil_div(N, 256), clusters = sms / 2;
     const int rounds2 = ceil_div(t2, clusters), rounds1 = ceil_div(m_tiles * ceil_div(N, 256), sms);
-    pair = t2 >= 4 * clusters && rounds2 <= rounds1 + (rounds1 >= 16 ? 1 : 0);
+    // measured (profiles/r01_kernel_microbench_v5.json): pairs win by 5-12 % once every pair has >= 4 tiles, and already at
+    // one tile per pair when the reduction is long (K >= 4096); small problems keep the single-CTA kernel's finer tiles
+    pair = rounds2 <= rounds1 + (rounds1 >= 16 ? 1 : 0) && (t2 >= 4 * clusters || (t2 >= clusters && K >= 4096));
   }
   if (pair) bn = 256;
   const int tiles = pair ? ceil_div(M, 2 * BM) * ceil_div(N, 256) : m_tiles * ceil_div(N, bn);
