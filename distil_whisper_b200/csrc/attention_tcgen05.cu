@@ -184,23 +184,48 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         for (int i = 0; i < 128; ++i)
           if (kbase + i >= lim) v[i] = __float_as_uint(-INFINITY);
       }
-      // row max with 8 independent chains (a single fmaxf chain would serialise 128 dependent 4-cycle ops)
-      float mxp[8];
+      // Row maximum: computed for the first tile only.  Later tiles run their exponentials against the running reference
+      // maximum m_ref straight away and look at the tile's row sum afterwards: a sum above 2^15 (some score more than
+      // ~2^8 above the reference; +inf on overflow) sends the row through the slow path -- true maximum, O and l brought
+      // to the new reference, exponentials redone (P has not been handed to the MMA warp yet).  That is the same "lazy
+      // rescale" rule as before, minus 128 FMNMX and their dependent chain on every tile's critical path.
+      auto row_max = [&]() {
+        float mxp[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) mxp[c] = __uint_as_float(v[c]);
+        for (int c = 0; c < 8; ++c) mxp[c] = __uint_as_float(v[c]);
 #pragma unroll
-      for (int i = 8; i < 128; i += 8) {
+        for (int i = 8; i < 128; i += 8) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) mxp[c] = fmaxf(mxp[c], __uint_as_float(v[i + c]));
-      }
-      const float mx = fmaxf(fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3])), fmaxf(fmaxf(mxp[4], mxp[5]), fmaxf(mxp[6], mxp[7])));
-      if (j == 0) {
-        m_ref = mx;
-      } else if ((mx - m_ref) * p.scale_log2 > 8.0f) {
-        // rare: bring O (TMEM) and l to the new reference maximum.  P V of tile j-1 must have landed first.
-        mbar_wait(o_full, (j - 1) & 1);
-        tc_fence_after();
+          for (int c = 0; c < 8; ++c) mxp[c] = fmaxf(mxp[c], __uint_as_float(v[i + c]));
+        }
+        return fmaxf(fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3])), fmaxf(fmaxf(mxp[4], mxp[5]), fmaxf(mxp[6], mxp[7])));
+      };
+      auto exp_tile = [&](float msc) {                      // P = 2^(s * scale_log2 - msc) -> TMEM; returns the row sum
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};                 // independent partial sums (no 128-long dependent FADD chain)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {                       // 64 keys -> 32 packed columns per tcgen05.st
+          uint32_t pk[32];
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) {
+            const float e0 = fast_exp2(fmaf(__uint_as_float(v[c * 64 + i]), p.scale_log2, -msc));
+            const float e1 = fast_exp2(fmaf(__uint_as_float(v[c * 64 + i + 1]), p.scale_log2, -msc));
+            ls[(i >> 1) & 3] += e0 + e1;
+            pk[i >> 1] = pack_bf16x2(e0, e1);
+          }
+          tmem_st_32x32(t_p + c * 32, pk);
+        }
+        return (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      };
+      if (j == 0) m_ref = row_max();
+      mbar_wait(p_empty, (j & 1) ^ 1);                      // P V of the previous tile has consumed P (and updated O)
+      tc_fence_after();
+      float tile_sum = exp_tile(m_ref * p.scale_log2);
+      if (__any_sync(0xffffffffu, !(tile_sum <= 32768.0f))) {
+        // rare, and taken by the whole warp (tcgen05.ld/st are warp-collective): bring O (TMEM) and l to the new reference
+        // maximum -- rows that did not need it keep theirs (f == 1); o_full(j-1) completed together with p_empty above
+        const float mx = fmaxf(m_ref, row_max());
         const float f = fast_exp2((m_ref - mx) * p.scale_log2);
+        tmem_st_wait();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t o[32];
@@ -210,30 +235,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
           tmem_st_32x32(t_o + c * 32, o);
         }
-        tmem_st_wait();
-        tc_fence_before();
         l_run *= f;
         m_ref = mx;
-      }
-      const float msc = m_ref * p.scale_log2;
-      mbar_wait(p_empty, (j & 1) ^ 1);                      // P V of the previous tile has consumed P
-      tc_fence_after();
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};          // independent partial sums (no 128-long dependent FADD chain)
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {                // 64 keys -> 32 packed columns per tcgen05.st
-        uint32_t pk[32];
-#pragma unroll
-        for (int i = 0; i < 64; i += 2) {
-          // (moving 1/8 of these to an FMA-pipe polynomial exp2 was measured: 0.572 vs 0.564 ms -- the MUFU pipe is not the limiter)
-          const float e0 = fast_exp2(fmaf(__uint_as_float(v[c * 64 + i]), p.scale_log2, -msc));
-          const float e1 = fast_exp2(fmaf(__uint_as_float(v[c * 64 + i + 1]), p.scale_log2, -msc));
-          ls[(i >> 1) & 3] += e0 + e1;
-          pk[i >> 1] = pack_bf16x2(e0, e1);
-        }
-        tmem_st_32x32(t_p + c * 32, pk);
+        tile_sum = exp_tile(m_ref * p.scale_log2);
       }
       tmem_st_wait();
-      l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      l_run += tile_sum;
       tc_fence_before();
       mbar_arrive(p_full);
     }

@@ -68,6 +68,31 @@ def test_attention_fwd_tcgen05(ops, B, H, Sq, Sk, causal):
     assert _rel(o, o2.float()) < 8e-3
 
 
+@pytest.mark.parametrize("growth", [3.0, -3.0, 0.0])
+def test_attention_fwd_tcgen05_reference_maximum_jumps(ops, growth):
+    """Scores whose row maximum climbs by ~2^30 from one 128-key tile to the next (growth > 0: every tile takes the kernel's
+    slow path -- row sum above 2^15 -> true maximum, O / l rescaled, exponentials redone), falls (growth < 0: later tiles
+    underflow against the first tile's reference) or sits at huge constant magnitude (0)."""
+    B, H, S = 2, 2, 700
+    d = H * 64
+    q = _randn((B * S, d), 21, 3.0, torch.bfloat16)
+    k = _randn((B * S, d), 22, 3.0, torch.bfloat16).float().view(B, S, d)
+    tile = (torch.arange(S, device="cuda") // 128).float()
+    if growth > 0:
+        k = k * (1.0 + tile)[None, :, None]
+    elif growth < 0:
+        k = k * (6.0 - tile)[None, :, None]
+    else:
+        k = k * 4.0
+    k = k.reshape(B * S, d).to(torch.bfloat16)
+    v = _randn((B * S, d), 23, 1.0, torch.bfloat16)
+    o, lse = ops.attention_fwd(q, k, v, B, H, S, S, False, use_tc=True)
+    o_ref, lse_ref = _sdpa_ref(q, k, v, B, H, S, S, False)
+    assert torch.isfinite(o.float()).all() and torch.isfinite(lse).all()
+    assert _rel(o, o_ref) < 1e-2, _rel(o, o_ref)
+    assert torch.allclose(lse, lse_ref, atol=5e-2, rtol=2e-4)
+
+
 @pytest.mark.parametrize("use_tc", [True, False])
 @pytest.mark.parametrize("B,H,Sq,Sk,causal", [(2, 2, 128, 128, True), (1, 2, 12, 12, True), (2, 2, 100, 300, False),
                                               (1, 1, 200, 1500, False), (2, 3, 70, 70, True), (1, 2, 1500, 1500, False),
