@@ -281,7 +281,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 }
 
 // [B, S, cols] view of a [B*S, ld] matrix as a 3-D tensor map; box = 64 columns x 128 rows x 1 batch, 128B swizzle
-static int make_tmap_bsc(CUtensorMap* out, const void* base, int64_t ld, int B, int S, int cols) {
+static int make_tmap_bsc(CUtensorMap* out, const void* base, int64_t ld, int B, int S, int cols, uint32_t box_rows = 128) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) { dwb_set_error("cuTensorMapEncodeTiled entry point unavailable"); return DWB_ERR_CUDA; }
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((ld * 2) & 15) != 0) {
@@ -290,7 +290,7 @@ static int make_tmap_bsc(CUtensorMap* out, const void* base, int64_t ld, int B, 
   }
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)S, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)S * (cuuint64_t)ld * 2};
-  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t box[3] = {64, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -329,7 +329,9 @@ extern "C" int dwb_attention_fwd_tc(const void* q, int64_t ldq, const void* k, i
   // (Two variants with two softmax threads per query row -- 16 softmax warps per SM -- were built and measured in round 1:
   //  with a per-tile pair barrier 0.70 ms, with each thread reducing the full-row maximum itself (no exchange) 0.62 ms,
   //  against 0.56 ms for this kernel: the XU pipe is busy 63 % of the time here, but the extra TMEM traffic and the
-  //  tighter register budget (104/thread) cost more than the additional warps recover.  See profiles/README.md.)
+  //  tighter register budget (104/thread) cost more than the additional warps recover.  A third variant with 64-key tiles
+  //  and double-buffered S / P in TMEM (QK^T two tiles ahead, no wait on P V) measured 0.60 ms: per-tile instruction and
+  //  barrier overhead, not the dependency chain, is what the power-capped SM pays for.  See profiles/README.md.)
   attn_fwd_tc_kernel<<<grid, TA_THREADS, TA_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, to, p);
   DWB_LAUNCH_OK();
   return DWB_OK;
