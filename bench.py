@@ -272,7 +272,7 @@ def main():
                    "parallelism": f"dp{world}", "l2": "working set >> 126 MB L2, no flush", "variant": "B (--freeze_encoder)" if args.variant == "B" else "A (trainable encoder)",
                    "algorithmic_tflop_per_utt": tf_per_utt},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "gemm_bf16_tcgen05_kernel (all launches of the timed region)",
+                     "traffic": traffic, "kernel": "gemm_bf16_2cta_kernel + gemm_bf16_tcgen05_kernel (every GEMM launch of the timed region)",
                      "peak_source": peak_src, "gemm_share_of_step": gemm_ms * 1e-3 / args.steps / sec_eager if sec_eager > 0 else None,
                      "measured_in": "eager replay of the same steps (ms_per_step_eager below)",
                      "gemm_launches": len(prof)},
