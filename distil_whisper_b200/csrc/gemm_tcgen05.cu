@@ -28,7 +28,7 @@ struct GemmCfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (192 * 1024) / kStageBytes;
-  static constexpr int kTmemCols = 2 * BN;   // double-buffered accumulator (power of two: 256 or 512)
+  static constexpr int kTmemCols = BN <= 128 ? 256 : 512;   // double-buffered accumulator (allocation must be a power of two)
   static constexpr int kUsedBytes = kStages * kStageBytes + 2 * kPanelBytes + 256 + 2 * BN * 4;
   static constexpr int kSmemBytes = 512 + kUsedBytes;    // 512 B of slack for rounding the base up to 1024 B (checked)
 };
@@ -672,24 +672,34 @@ extern "C" int dwb_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const v
   // tile shape / split-K heuristic: fill 148 SMs in as few full waves as possible
   const int sms = num_sms();
   const int m_tiles = ceil_div(M, BM);
-  // 128x256 tiles feed the tensor pipe at 96 B/clk of smem reads; 128x128 tiles need 128 B/clk (the smem limit) and top
-  // out near 60 % of peak, so they are only worth it when they fix a badly quantised last wave (small problems).
+  // 128x256 tiles feed the tensor pipe at 96 B/clk of smem reads; 128x128 tiles need 128 B/clk (the smem limit) and reach
+  // ~70 % of the 256-wide rate, 128x192 sits in between.  Pick the width whose (rounds x cost of one tile) is smallest:
+  // e.g. the decoder's 4096x1280 outputs are 160 256-wide tiles = two rounds on 148 SMs, but 224 192-wide tiles = two
+  // rounds of 3/4 the work.
   int bn = 256;
+  double best_single = 1e30;
   {
-    const int t256 = m_tiles * ceil_div(N, 256), t128 = m_tiles * ceil_div(N, 128);
-    const double w256 = (double)ceil_div(t256, sms) * 1.0, w128 = (double)ceil_div(t128, sms) * 0.8;
-    if (N <= 128 || w128 < w256) bn = 128;
+    const int cand[3] = {256, 192, 128};
+    const double cost[3] = {1.0, 0.78, 0.72};
+    double best = 1e30;
+    for (int i = 0; i < 3; ++i) {
+      if (cand[i] != 128 && N <= 128) continue;
+      const double w = (double)ceil_div(m_tiles * ceil_div(N, cand[i]), sms) * cost[i];
+      if (w < best - 1e-9) { best = w; bn = cand[i]; }
+    }
+    best_single = best;
   }
   // CTA pairs (256 x 256 tiles, 74 clusters): worth it when the problem fills the pairs for several rounds
   static const int pair_env = [] { const char* e = getenv("DWB_GEMM_2CTA"); return e ? atoi(e) : 1; }();
   bool pair = false;
   if (impl == 2) pair = true;
-  else if (impl == 0 && pair_env && bn == 256 && N >= 256) {
+  else if (impl == 0 && pair_env && N >= 256) {
     const int t2 = ceil_div(M, 2 * BM) * ceil_div(N, 256), clusters = sms / 2;
-    const int rounds2 = ceil_div(t2, clusters), rounds1 = ceil_div(m_tiles * ceil_div(N, 256), sms);
-    // measured (profiles/r01_kernel_microbench_v5.json): pairs win by 5-12 % once every pair has >= 4 tiles, and already at
-    // one tile per pair when the reduction is long (K >= 4096); small problems keep the single-CTA kernel's finer tiles
-    pair = rounds2 <= rounds1 + (rounds1 >= 16 ? 1 : 0) && (t2 >= 4 * clusters || (t2 >= clusters && K >= 4096));
+    // measured (profiles/r01_kernel_microbench_v5/v6.json): a pair finishes its 256x256 tile 5-12 % sooner than two single
+    // CTAs finish their 128x256 tiles once it has >= 8 tiles to walk (M = 48000 shapes, LM head); with fewer tiles the
+    // 128x192 single-CTA tiling quantises better (decoder shapes), except for very long reductions (LM-head dgrad)
+    const double pair_cost = (double)ceil_div(t2, clusters) * 0.92;
+    pair = (t2 >= 8 * clusters && pair_cost <= best_single + 1e-9) || (t2 >= clusters && K >= 16384);
   }
   if (pair) bn = 256;
   const int tiles = pair ? ceil_div(M, 2 * BM) * ceil_div(N, 256) : m_tiles * ceil_div(N, bn);
@@ -735,8 +745,12 @@ extern "C" int dwb_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const v
     }
   }
   const int grid = items < sms ? items : sms;
-  const int key = (bn == 256 ? 4 : 0) | (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
+  const int key = (bn == 256 ? 4 : bn == 192 ? 8 : 0) | (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
   switch (key) {
+    case 8: return launch_gemm<192, 0, 0>(ta, tb, tc, p, grid, st);
+    case 9: return launch_gemm<192, 0, 1>(ta, tb, tc, p, grid, st);
+    case 10: return launch_gemm<192, 1, 0>(ta, tb, tc, p, grid, st);
+    case 11: return launch_gemm<192, 1, 1>(ta, tb, tc, p, grid, st);
     case 0: return launch_gemm<128, 0, 0>(ta, tb, tc, p, grid, st);
     case 1: return launch_gemm<128, 0, 1>(ta, tb, tc, p, grid, st);
     case 2: return launch_gemm<128, 1, 0>(ta, tb, tc, p, grid, st);

@@ -30,6 +30,7 @@ def bench_gemm():
         (48000, 1280, 5120, 0, 0, 0, 0), (48000, 2560, 1280, 0, 0, 0, 0), (4096, 1280, 1280, 0, 0, 0, 0),
         (4096, 5120, 1280, 0, 0, 1, 0), (4096, 51866, 1280, 0, 0, 0, 1), (4096, 1280, 51866, 0, 1, 0, 0),
         (1280, 1280, 4096, 1, 1, 0, 1), (51866, 1280, 4096, 1, 1, 0, 1), (8192, 8192, 8192, 0, 0, 0, 0),
+        (4096, 3840, 1280, 0, 0, 0, 0), (4096, 1280, 5120, 0, 0, 0, 0), (5120, 1280, 4096, 1, 1, 0, 1),
     ]:
         def mk(r, c):
             return torch.randn((r, ops.round_up(c, 8)), device="cuda").bfloat16()[:, :c]
