@@ -11,7 +11,8 @@ constexpr int LN_MAX_VEC = 16;   // float4 per lane: d <= 16*4*32 = 2048
 // x_new = x_in[row % x_rows_mod] (+ y);  ln = LayerNorm(x_new) * gamma + beta
 // HF:models/whisper/modeling_whisper.py:393-409 / :470-503 residual adds followed by the next pre-LN, and
 // :623-625 (the conv stem output plus the positional table feeding layer 0's LN) are all this one pattern.
-__global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restrict__ x_in, int x_rows_mod,
+template <int NV, int MINB>
+__global__ void __launch_bounds__(256, MINB) add_layernorm_kernel(const float* __restrict__ x_in, int x_rows_mod,
                                                             const bf16* __restrict__ y, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float* __restrict__ x_out,
                                                             bf16* __restrict__ ln_out, float* __restrict__ mean_out,
@@ -24,10 +25,10 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
   const float4* xr = reinterpret_cast<const float4*>(x_in + (int64_t)src_row * d);
   const uint2* yr = y ? reinterpret_cast<const uint2*>(y + (int64_t)row * d) : nullptr;
   const int nvec = d >> 2;
-  float4 v[LN_MAX_VEC];
+  float4 v[NV];   // NV = float4 per lane, sized to the row (register budget decides how many rows an SM keeps in flight)
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int idx = i * 32 + lane;
     if (idx < nvec) {
       float4 a = xr[idx];
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
   const float mean = warp_sum(sum) / (float)d;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int idx = i * 32 + lane;
     if (idx < nvec) {
       const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int idx = i * 32 + lane;
     if (idx < nvec) {
       if (xo) xo[idx] = v[i];
@@ -346,8 +347,21 @@ extern "C" int dwb_add_layernorm(const float* x_in, int x_rows_mod, const void* 
                                  void* stream) {
   DWB_CHECK_ARG(x_in && gamma && beta, "dwb_add_layernorm: null operand");
   DWB_CHECK_ARG(rows > 0 && d > 0 && (d % 4) == 0 && d <= LN_MAX_VEC * 128, "dwb_add_layernorm: d=%d unsupported", d);
-  add_layernorm_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(x_in, x_rows_mod, (const bf16*)y_bf16, gamma, beta, x_out,
-                                                                            (bf16*)ln_out_bf16, mean_out, rstd_out, rows, d, eps);
+  const int nvec = ceil_div(d, 128);
+  const dim3 grid(ceil_div(rows, 8));
+  cudaStream_t st = (cudaStream_t)stream;
+#define DWB_LN_LAUNCH(NV, MINB)                                                                                              \
+  add_layernorm_kernel<NV, MINB><<<grid, 256, 0, st>>>(x_in, x_rows_mod, (const bf16*)y_bf16, gamma, beta, x_out, (bf16*)ln_out_bf16, \
+                                                       mean_out, rstd_out, rows, d, eps)
+  static const int wide_only = [] { const char* e = getenv("DWB_LN_WIDE"); return e ? atoi(e) : 0; }();   // A/B switch for the microbench
+  if (wide_only) DWB_LN_LAUNCH(16, 2);
+  else if (nvec <= 3) DWB_LN_LAUNCH(3, 4);
+  else if (nvec <= 4) DWB_LN_LAUNCH(4, 4);
+  else if (nvec <= 6) DWB_LN_LAUNCH(6, 4);
+  else if (nvec <= 8) DWB_LN_LAUNCH(8, 4);
+  else if (nvec <= 10) DWB_LN_LAUNCH(10, 4);
+  else DWB_LN_LAUNCH(16, 2);
+#undef DWB_LN_LAUNCH
   DWB_LAUNCH_OK();
   return DWB_OK;
 }

@@ -126,6 +126,24 @@ def bench_logmel():
     return out
 
 
+def bench_ln():
+    out = []
+    for rows, d in [(48000, 1280), (4096, 1280)]:
+        x = torch.randn((rows, d), device="cuda")
+        g, b = torch.ones(d, device="cuda"), torch.zeros(d, device="cuda")
+        bufs = [torch.randn((rows, d), device="cuda") for _ in range(3)]      # rotate inputs: 3 x 245 MB > L2
+        it = [0]
+
+        def run():
+            it[0] += 1
+            ops.add_layernorm(bufs[it[0] % 3], None, g, b, rows=rows, d=d, write_x=False, write_ln=True)
+        ms = timeit(run, iters=12)
+        nbytes = rows * d * 6
+        out.append(dict(rows=rows, d=d, ms=round(ms, 4), gbps=round(nbytes / ms / 1e6, 1)))
+        print(out[-1], flush=True)
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "attn", "logmel"]
     res = {}
@@ -137,6 +155,8 @@ if __name__ == "__main__":
         res["attn_bwd"] = bench_attn_bwd()
     if "logmel" in which:
         res["logmel"] = bench_logmel()
+    if "ln" in which:
+        res["ln"] = bench_ln()
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/bench_kernels.json", "w") as f:
         json.dump(res, f, indent=1)
