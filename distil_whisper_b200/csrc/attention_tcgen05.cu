@@ -331,7 +331,11 @@ extern "C" int dwb_attention_fwd_tc(const void* q, int64_t ldq, const void* k, i
   //  against 0.56 ms for this kernel: the XU pipe is busy 63 % of the time here, but the extra TMEM traffic and the
   //  tighter register budget (104/thread) cost more than the additional warps recover.  A third variant with 64-key tiles
   //  and double-buffered S / P in TMEM (QK^T two tiles ahead, no wait on P V) measured 0.60 ms: per-tile instruction and
-  //  barrier overhead, not the dependency chain, is what the power-capped SM pays for.  See profiles/README.md.)
+  //  barrier overhead, not the dependency chain, is what the power-capped SM pays for.  A fourth, FA4-shaped kernel -- one
+  //  CTA per SM owning two query tiles (512 TMEM columns), K/V loaded once for both, optional named-barrier ping-pong of the
+  //  two softmax warpgroups -- measured 0.63 ms with and without the ping-pong: one MMA-issuing thread serving two tiles in
+  //  program order and a single softmax warp per SM sub-partition on the XU pipe at a time are both worse than two
+  //  independent CTAs.  See profiles/README.md.)
   attn_fwd_tc_kernel<<<grid, TA_THREADS, TA_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, to, p);
   DWB_LAUNCH_OK();
   return DWB_OK;

@@ -329,6 +329,10 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // UMMA descriptors (sm_100): see DESIGN.md "tcgen05 operand layouts"
 //   K-major  SW128: rows of 64 bf16 (128 B), 8-row swizzle atoms stacked every 1024 B (SBO); LBO unused.
