@@ -365,8 +365,10 @@ def _abi_call_conv_wgrad(gkc, dw, O, Cc):
 
 # =================================================================================================================
 # decoder
-def decoder_forward(st: _State, ids, enc, B, S, save):
-    """ids [B, T] int64, enc bf16 [B*S, d] -> (final LayerNorm output bf16 [B*T, d], ctx for the backward)."""
+def decoder_forward(st: _State, ids, enc, B, S, save, cross_kv=None):
+    """ids [B, T] int64, enc bf16 [B*S, d] -> (final LayerNorm output bf16 [B*T, d], ctx for the backward).
+    cross_kv: optional dict filled with / read from the per-layer cross-attention K/V projections of `enc` (they do not
+    depend on the decoder inputs, so greedy decoding projects the 1500 encoder positions once, not once per token)."""
     dec = st.m
     cfg = dec.config
     d, H, T = cfg.d_model, cfg.decoder_attention_heads, ids.shape[1]
@@ -397,7 +399,12 @@ def decoder_forward(st: _State, ids, enc, B, S, save):
         g, b_ = _ln(st, k + ".ln2", layer.encoder_attn_layer_norm)
         x2, h2, mu2, rs2 = ops.add_layernorm(x1, y1, g, b_, rows=M, d=d, save_stats=save)
         qc = ops.gemm(h2, wc["wq"], bias=wc["bq"])
-        kvc = ops.gemm(enc, wc["wkv"], bias=wc["bkv"])                                  # [B*S, 2d]
+        if cross_kv is not None and i in cross_kv:
+            kvc = cross_kv[i]
+        else:
+            kvc = ops.gemm(enc, wc["wkv"], bias=wc["bkv"])                              # [B*S, 2d]
+            if cross_kv is not None:
+                cross_kv[i] = kvc
         o2, lse2 = ops.attention_fwd(qc, kvc[:, :d], kvc[:, d:], B, H, T, S, causal=False, need_lse=save, use_tc=USE_TC_ATTENTION)
         y2 = ops.gemm(o2, wc["wo"], bias=wc["bo"])
         # --- MLP

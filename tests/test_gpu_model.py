@@ -238,3 +238,37 @@ def test_cuda_graph_replay_matches_eager():
         opt_e.step()
         opt_g.step()
     assert _rel(opt_g.flat.data, opt_e.flat.data) < 1e-5
+
+
+def test_greedy_generate_follows_the_oracle_argmax():
+    """generate() (ref:training/run_distillation.py:1526 eval path, greedy): every token it emits must be the oracle's
+    arg-max on the same prefix, up to the bf16 logit tolerance (random-init logits have small top-2 margins, so the check
+    is 'the oracle's logit of our token is within tolerance of the oracle's maximum', position by position); rows stop at
+    EOS and are padded; the prompt is preserved; unsupported decoding modes raise."""
+    sc = wo.PRESETS["tiny-student"]
+    sd = wo.init_state_dict(sc, 5)
+    m = _build(sc, sd)
+    batch = wo.synthetic_batch(sc, batch=3, n_tok=4, seed=17)
+    feats = batch["input_features"]
+    prompt = torch.tensor([[sc.decoder_start_token_id, 7], [sc.decoder_start_token_id, 11], [sc.decoder_start_token_id, 3]])
+    out = m.generate(feats.cuda(), decoder_input_ids=prompt.cuda(), max_new_tokens=10, eos_token_id=10 ** 6)   # eos never hit
+    assert out.shape == (3, 12) and out.dtype == torch.long
+    assert torch.equal(out[:, :2].cpu(), prompt)
+    with torch.no_grad():
+        ref = wo.model_forward(sd, sc, input_features=feats, decoder_input_ids=out[:, :-1].cpu())["logits"]
+    tol = LOGITS_REL * float(ref.abs().max())
+    for t in range(1, out.shape[1] - 1):
+        chosen = ref[torch.arange(3), t, out[:, t + 1].cpu()]
+        assert (chosen >= ref[:, t].max(-1).values - tol).all(), t
+    # EOS handling: declare the first generated token of row 0 to be EOS -> the rest of that row is padding
+    eos = int(out[0, 2])
+    out2 = m.generate(feats.cuda(), decoder_input_ids=prompt.cuda(), max_new_tokens=6, eos_token_id=eos, pad_token_id=0)
+    assert int(out2[0, 2]) == eos and (out2[0, 3:] == 0).all()
+    # default prompt = decoder_start_token_id, max_length from the config; training mode is restored
+    m.train()
+    out3 = m.generate(feats.cuda(), max_length=5)
+    assert out3.shape[1] <= 5 and (out3[:, 0] == sc.decoder_start_token_id).all() and m.training
+    with pytest.raises(NotImplementedError):
+        m.generate(feats.cuda(), num_beams=4)
+    with pytest.raises(NotImplementedError):
+        m.generate(feats.cuda(), return_timestamps=True)
