@@ -97,3 +97,15 @@ def test_feature_extractor_host_side():
 
 def test_sinusoids_closed_form():
     assert torch.allclose(sinusoids(1500, 1280), wo.sinusoids(1500, 1280))
+
+
+def test_generate_rejects_unsupported_decoding_modes_before_touching_the_device():
+    """generate() is greedy only (ref:training/run_distillation.py:1526 with its default gen_kwargs); anything else must
+    raise instead of silently decoding differently -- checked here without a GPU because the argument screen comes first."""
+    import pytest
+    from distil_whisper_b200.modeling import DistilWhisperB200ForConditionalGeneration
+    m = DistilWhisperB200ForConditionalGeneration(wo.PRESETS["tiny-student"].to_dict())
+    feats = torch.zeros((1, 80, 100))
+    for kw in (dict(num_beams=4), dict(do_sample=True), dict(return_timestamps=True), dict(forced_decoder_ids=[(1, 2)])):
+        with pytest.raises(NotImplementedError):
+            m.generate(feats, **kw)
