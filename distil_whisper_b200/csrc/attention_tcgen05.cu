@@ -201,20 +201,26 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         return fmaxf(fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3])), fmaxf(fmaxf(mxp[4], mxp[5]), fmaxf(mxp[6], mxp[7])));
       };
       auto exp_tile = [&](float msc) {                      // P = 2^(s * scale_log2 - msc) -> TMEM; returns the row sum
-        float ls[4] = {0.f, 0.f, 0.f, 0.f};                 // independent partial sums (no 128-long dependent FADD chain)
+        // packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2): one instruction scales two scores, one accumulates two
+        // exponentials -- 2.5 instructions per exponential instead of 3.5 around the 8-cycle MUFU cadence
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-msc, -msc);
+        float2 ls[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
         for (int c = 0; c < 2; ++c) {                       // 64 keys -> 32 packed columns per tcgen05.st
           uint32_t pk[32];
 #pragma unroll
           for (int i = 0; i < 64; i += 2) {
-            const float e0 = fast_exp2(fmaf(__uint_as_float(v[c * 64 + i]), p.scale_log2, -msc));
-            const float e1 = fast_exp2(fmaf(__uint_as_float(v[c * 64 + i + 1]), p.scale_log2, -msc));
-            ls[(i >> 1) & 3] += e0 + e1;
-            pk[i >> 1] = pack_bf16x2(e0, e1);
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[c * 64 + i]), __uint_as_float(v[c * 64 + i + 1])), sc2, nm2);
+            float2 e;
+            e.x = fast_exp2(x.x);
+            e.y = fast_exp2(x.y);
+            ls[(i >> 1) & 3] = __fadd2_rn(ls[(i >> 1) & 3], e);
+            pk[i >> 1] = pack_bf16x2(e.x, e.y);
           }
           tmem_st_32x32(t_p + c * 32, pk);
         }
-        return (ls[0] + ls[1]) + (ls[2] + ls[3]);
+        const float2 t = __fadd2_rn(__fadd2_rn(ls[0], ls[1]), __fadd2_rn(ls[2], ls[3]));
+        return t.x + t.y;
       };
       if (j == 0) m_ref = row_max();
       mbar_wait(p_empty, (j & 1) ^ 1);                      // P V of the previous tile has consumed P (and updated O)
