@@ -97,6 +97,20 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
   return fmaf(-fabsf(x), e, fmaxf(x, 0.0f));
 }
+// two elements at a time with the sm_100 packed fp32x2 FMA (FFMA2): the Horner chain costs 6 instructions per PAIR
+__device__ __forceinline__ float2 gelu_erf_fast2(float2 x) {
+  const float2 t = make_float2(fminf(fabsf(x.x), 6.0f), fminf(fabsf(x.y), 6.0f));
+  float2 q = __ffma2_rn(make_float2(3.309327075839974e-05f, 3.309327075839974e-05f), t, make_float2(-0.0007692237268202007f, -0.0007692237268202007f));
+  q = __ffma2_rn(q, t, make_float2(0.00808072928339243f, 0.00808072928339243f));
+  q = __ffma2_rn(q, t, make_float2(-0.05341212451457977f, -0.05341212451457977f));
+  q = __ffma2_rn(q, t, make_float2(-0.4587709605693817f, -0.4587709605693817f));
+  q = __ffma2_rn(q, t, make_float2(-1.1512017250061035f, -1.1512017250061035f));
+  q = __ffma2_rn(q, t, make_float2(-0.999993085861206f, -0.999993085861206f));
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q.y));
+  return make_float2(fmaf(-fabsf(x.x), e0, fmaxf(x.x, 0.0f)), fmaf(-fabsf(x.y), e1, fmaxf(x.y, 0.0f)));
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
   const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);

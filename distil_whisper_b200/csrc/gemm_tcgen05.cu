@@ -226,31 +226,32 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (lane == 0) tma_store_wait_read<1>();  // this warp's store from two panels ago has left the buffer
         __syncwarp();
         const float4* sb4 = reinterpret_cast<const float4*>(sb + c0);
+        const float2 alpha2 = make_float2(p.alpha, p.alpha);   // packed fp32x2 epilogue math (FFMA2): half the FMA instructions
         if (p.c_f32) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {           // 8 x 16 B chunks (4 fp32) per 128 B row
             const float4 bb = sb4[j];
-            float f0 = fmaf(__uint_as_float(v[j * 4 + 0]), p.alpha, bb.x), f1 = fmaf(__uint_as_float(v[j * 4 + 1]), p.alpha, bb.y);
-            float f2 = fmaf(__uint_as_float(v[j * 4 + 2]), p.alpha, bb.z), f3 = fmaf(__uint_as_float(v[j * 4 + 3]), p.alpha, bb.w);
-            if (p.act == 1) { f0 = gelu_erf_fast(f0); f1 = gelu_erf_fast(f1); f2 = gelu_erf_fast(f2); f3 = gelu_erf_fast(f3); }
-            st_shared_v4(row_saddr + buf_off + ((j ^ sw) << 4), __float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2),
-                         __float_as_uint(f3));
+            float2 g0 = __ffma2_rn(make_float2(__uint_as_float(v[j * 4 + 0]), __uint_as_float(v[j * 4 + 1])), alpha2, make_float2(bb.x, bb.y));
+            float2 g1 = __ffma2_rn(make_float2(__uint_as_float(v[j * 4 + 2]), __uint_as_float(v[j * 4 + 3])), alpha2, make_float2(bb.z, bb.w));
+            if (p.act == 1) { g0 = gelu_erf_fast2(g0); g1 = gelu_erf_fast2(g1); }
+            st_shared_v4(row_saddr + buf_off + ((j ^ sw) << 4), __float_as_uint(g0.x), __float_as_uint(g0.y), __float_as_uint(g1.x),
+                         __float_as_uint(g1.y));
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {           // 8 x 16 B chunks (8 bf16) per 128 B row
             const float4 b0 = sb4[2 * j], b1 = sb4[2 * j + 1];
-            float f[8];
-            f[0] = fmaf(__uint_as_float(v[j * 8 + 0]), p.alpha, b0.x); f[1] = fmaf(__uint_as_float(v[j * 8 + 1]), p.alpha, b0.y);
-            f[2] = fmaf(__uint_as_float(v[j * 8 + 2]), p.alpha, b0.z); f[3] = fmaf(__uint_as_float(v[j * 8 + 3]), p.alpha, b0.w);
-            f[4] = fmaf(__uint_as_float(v[j * 8 + 4]), p.alpha, b1.x); f[5] = fmaf(__uint_as_float(v[j * 8 + 5]), p.alpha, b1.y);
-            f[6] = fmaf(__uint_as_float(v[j * 8 + 6]), p.alpha, b1.z); f[7] = fmaf(__uint_as_float(v[j * 8 + 7]), p.alpha, b1.w);
+            float2 g[4];
+            g[0] = __ffma2_rn(make_float2(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1])), alpha2, make_float2(b0.x, b0.y));
+            g[1] = __ffma2_rn(make_float2(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3])), alpha2, make_float2(b0.z, b0.w));
+            g[2] = __ffma2_rn(make_float2(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5])), alpha2, make_float2(b1.x, b1.y));
+            g[3] = __ffma2_rn(make_float2(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7])), alpha2, make_float2(b1.z, b1.w));
             if (p.act == 1) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = gelu_erf_fast(f[e]);
+              for (int e = 0; e < 4; ++e) g[e] = gelu_erf_fast2(g[e]);
             }
-            st_shared_v4(row_saddr + buf_off + ((j ^ sw) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                         pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            st_shared_v4(row_saddr + buf_off + ((j ^ sw) << 4), pack_bf16x2(g[0].x, g[0].y), pack_bf16x2(g[1].x, g[1].y),
+                         pack_bf16x2(g[2].x, g[2].y), pack_bf16x2(g[3].x, g[3].y));
           }
         }
         fence_proxy_async_smem();
@@ -475,31 +476,32 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         if (lane == 0) tma_store_wait_read<1>();
         __syncwarp();
         const float4* sb4 = reinterpret_cast<const float4*>(sb + c0);
+        const float2 alpha2 = make_float2(p.alpha, p.alpha);   // packed fp32x2 epilogue math (FFMA2): half the FMA instructions
         if (p.c_f32) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 bb = sb4[j];
-            float f0 = fmaf(__uint_as_float(v[j * 4 + 0]), p.alpha, bb.x), f1 = fmaf(__uint_as_float(v[j * 4 + 1]), p.alpha, bb.y);
-            float f2 = fmaf(__uint_as_float(v[j * 4 + 2]), p.alpha, bb.z), f3 = fmaf(__uint_as_float(v[j * 4 + 3]), p.alpha, bb.w);
-            if (p.act == 1) { f0 = gelu_erf_fast(f0); f1 = gelu_erf_fast(f1); f2 = gelu_erf_fast(f2); f3 = gelu_erf_fast(f3); }
-            st_shared_v4(row_saddr + buf_off + ((j ^ sw) << 4), __float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2),
-                         __float_as_uint(f3));
+            float2 g0 = __ffma2_rn(make_float2(__uint_as_float(v[j * 4 + 0]), __uint_as_float(v[j * 4 + 1])), alpha2, make_float2(bb.x, bb.y));
+            float2 g1 = __ffma2_rn(make_float2(__uint_as_float(v[j * 4 + 2]), __uint_as_float(v[j * 4 + 3])), alpha2, make_float2(bb.z, bb.w));
+            if (p.act == 1) { g0 = gelu_erf_fast2(g0); g1 = gelu_erf_fast2(g1); }
+            st_shared_v4(row_saddr + buf_off + ((j ^ sw) << 4), __float_as_uint(g0.x), __float_as_uint(g0.y), __float_as_uint(g1.x),
+                         __float_as_uint(g1.y));
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b0 = sb4[2 * j], b1 = sb4[2 * j + 1];
-            float f[8];
-            f[0] = fmaf(__uint_as_float(v[j * 8 + 0]), p.alpha, b0.x); f[1] = fmaf(__uint_as_float(v[j * 8 + 1]), p.alpha, b0.y);
-            f[2] = fmaf(__uint_as_float(v[j * 8 + 2]), p.alpha, b0.z); f[3] = fmaf(__uint_as_float(v[j * 8 + 3]), p.alpha, b0.w);
-            f[4] = fmaf(__uint_as_float(v[j * 8 + 4]), p.alpha, b1.x); f[5] = fmaf(__uint_as_float(v[j * 8 + 5]), p.alpha, b1.y);
-            f[6] = fmaf(__uint_as_float(v[j * 8 + 6]), p.alpha, b1.z); f[7] = fmaf(__uint_as_float(v[j * 8 + 7]), p.alpha, b1.w);
+            float2 g[4];
+            g[0] = __ffma2_rn(make_float2(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1])), alpha2, make_float2(b0.x, b0.y));
+            g[1] = __ffma2_rn(make_float2(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3])), alpha2, make_float2(b0.z, b0.w));
+            g[2] = __ffma2_rn(make_float2(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5])), alpha2, make_float2(b1.x, b1.y));
+            g[3] = __ffma2_rn(make_float2(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7])), alpha2, make_float2(b1.z, b1.w));
             if (p.act == 1) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = gelu_erf_fast(f[e]);
+              for (int e = 0; e < 4; ++e) g[e] = gelu_erf_fast2(g[e]);
             }
-            st_shared_v4(row_saddr + buf_off + ((j ^ sw) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                         pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            st_shared_v4(row_saddr + buf_off + ((j ^ sw) << 4), pack_bf16x2(g[0].x, g[0].y), pack_bf16x2(g[1].x, g[1].y),
+                         pack_bf16x2(g[2].x, g[2].y), pack_bf16x2(g[3].x, g[3].y));
           }
         }
         fence_proxy_async_smem();
