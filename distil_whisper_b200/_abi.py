@@ -22,6 +22,8 @@ SIGNATURES = {
     "dwb_last_error": (C.c_char_p, []),
     "dwb_abi_version": (_i, []),
     "dwb_check_device": (_i, []),
+    "dwb_launch_count": (_l, [_i]),
+    "dwb_scale_bf16_dev": (_i, [_p, _l, _p, _p]),
     "dwb_gemm_bf16": (_i, [_p, _l, _i, _p, _l, _i, _p, _l, _i, _i, _i, _i, _p, _i, _f, _i, _i, _p]),
     "dwb_attention_fwd": (_i, [_p, _l, _p, _l, _p, _l, _p, _l, _p, _i, _i, _i, _i, _i, _i, _f, _p]),
     "dwb_attention_fwd_tc": (_i, [_p, _l, _p, _l, _p, _l, _p, _l, _p, _i, _i, _i, _i, _i, _i, _f, _p]),
@@ -52,7 +54,7 @@ SIGNATURES = {
     "dwb_logmel": (_i, [_p, _p, _i, _i, _p, _p]),
 }
 
-_NO_STATUS = {"dwb_last_error", "dwb_abi_version", "dwb_kd_loss_workspace_bytes"}
+_NO_STATUS = {"dwb_last_error", "dwb_abi_version", "dwb_kd_loss_workspace_bytes", "dwb_launch_count"}
 
 
 class DwbError(RuntimeError):
@@ -68,10 +70,9 @@ def header_symbols(path: str = HEADER_PATH):
 
 _lib = None
 
-# kernel launches issued through the ABI (bench.py reads / resets LAUNCHES[0]); entry -> kernels it launches
-LAUNCHES = [0]
-_KERNELS_PER_CALL = {"dwb_attention_bwd": 2, "dwb_attention_bwd_tc": 2, "dwb_kd_loss": 3, "dwb_last_error": 0, "dwb_abi_version": 0, "dwb_check_device": 0,
-                     "dwb_kd_loss_workspace_bytes": 0, "dwb_logmel_plan_create": 0, "dwb_logmel_plan_destroy": 0}
+def launch_count(reset: bool = False) -> int:
+    """Kernel launches issued by libdwb.so since the last reset (counted inside the library at every <<<>>>)."""
+    return int(load().dwb_launch_count(1 if reset else 0))
 
 
 def load() -> C.CDLL:
@@ -96,7 +97,6 @@ def call(name: str, *args):
     """Invoke an entry point; non-zero status -> DwbError carrying dwb_last_error()."""
     lib = load()
     rc = getattr(lib, name)(*args)
-    LAUNCHES[0] += _KERNELS_PER_CALL.get(name, 1)
     if name in _NO_STATUS:
         return rc
     if rc != 0:

@@ -13,7 +13,16 @@ extern "C" void dwb_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* dwb_last_error(void) { return g_err; }
-extern "C" int dwb_abi_version(void) { return 1; }
+extern "C" int dwb_abi_version(void) { return 2; }
+
+// kernel launches issued by this library since the last reset (host-side count of <<<>>> launches; a CUDA-graph replay
+// re-launches the captured kernels without passing through here)
+static unsigned long long g_launches = 0;
+extern "C" void dwb_count_launch(void) { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+extern "C" int64_t dwb_launch_count(int reset) {
+  const unsigned long long v = reset ? __atomic_exchange_n(&g_launches, 0ull, __ATOMIC_RELAXED) : __atomic_load_n(&g_launches, __ATOMIC_RELAXED);
+  return (int64_t)v;
+}
 
 // 0 when a compute-capability 10.x device is current; error otherwise (the product never falls back to a CPU path)
 extern "C" int dwb_check_device(void) {

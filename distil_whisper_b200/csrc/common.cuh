@@ -31,7 +31,13 @@ extern "C" void dwb_set_error(const char* fmt, ...);
     }                                                                                  \
   } while (0)
 
-#define DWB_LAUNCH_OK() DWB_CUDA_OK(cudaGetLastError())
+// every kernel launch of the library passes through here: the counter is what bench.py reports as `gpu_launches`
+extern "C" void dwb_count_launch(void);
+#define DWB_LAUNCH_OK()               \
+  do {                                \
+    dwb_count_launch();               \
+    DWB_CUDA_OK(cudaGetLastError()); \
+  } while (0)
 
 typedef __nv_bfloat16 bf16;
 

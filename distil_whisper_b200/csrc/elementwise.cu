@@ -254,11 +254,13 @@ __global__ void embed_fwd_kernel(const int64_t* __restrict__ ids, const TE* __re
                                  float* __restrict__ x, int rows, int T, int d, int vocab) {
   const int row = blockIdx.x;
   if (row >= rows) return;
-  int64_t id = ids[row];
-  if (id < 0 || id >= vocab) id = 0;   // ids are validated on the host; never index out of bounds
+  const int64_t id = ids[row];
   const int t = row % T;
+  // nn.Embedding raises on an out-of-range id (device assert); here the row is poisoned with NaN so that the loss and
+  // every gradient of the step become NaN instead of silently decoding token 0 -- never an out-of-bounds read
+  const bool ok = id >= 0 && id < vocab;
   for (int c = threadIdx.x; c < d; c += blockDim.x)
-    x[(int64_t)row * d + c] = (float)E[id * d + c] + (float)P[(int64_t)t * d + c];
+    x[(int64_t)row * d + c] = ok ? (float)E[id * d + c] + (float)P[(int64_t)t * d + c] : __int_as_float(0x7fc00000);
 }
 // dE[ids] += dx (skipping padding_idx), dP[t] += dx
 __global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ dx, float* __restrict__ dE,
@@ -332,6 +334,23 @@ __global__ void gelu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ y
   }
 }
 
+// x *= *scale for a contiguous bf16 buffer (n % 8 == 0); every thread leaves at once when *scale == 1 -- the upstream
+// gradient `loss.backward()` supplies -- so the common case costs one empty launch, not a pass over HBM
+__global__ void __launch_bounds__(256) scale_bf16_dev_kernel(bf16* __restrict__ x, int64_t n8, const float* __restrict__ scale) {
+  const float s = *scale;
+  if (s == 1.0f) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    uint4 v = reinterpret_cast<uint4*>(x)[i];
+    uint32_t* u = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(u[j]);
+      u[j] = pack_bf16x2(f.x * s, f.y * s);
+    }
+    reinterpret_cast<uint4*>(x)[i] = v;
+  }
+}
+
 static inline int grid_for(int64_t work_items, int threads) {
   int64_t g = ceil_div64(work_items, threads);
   const int64_t cap = (int64_t)kNumSMs * 16;
@@ -393,6 +412,13 @@ extern "C" int dwb_cast_f32_to_bf16(const float* src, int64_t lds, void* dst, in
                 "dwb_cast_f32_to_bf16: bad shape/alignment rows=%d cols=%d", rows, cols);
   cast_f32_bf16_kernel<<<grid_for((int64_t)rows * cols / 4, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, (bf16*)dst, ldd, rows, cols,
                                                                                                   scale);
+  DWB_LAUNCH_OK();
+  return DWB_OK;
+}
+extern "C" int dwb_scale_bf16_dev(void* x_bf16, int64_t n, const float* scale_dev, void* stream) {
+  DWB_CHECK_ARG(x_bf16 && scale_dev && n > 0 && (n % 8) == 0 && (reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0,
+                "dwb_scale_bf16_dev: bad args (n=%lld must be a multiple of 8, 16 B aligned)", (long long)n);
+  scale_bf16_dev_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((bf16*)x_bf16, n / 8, scale_dev);
   DWB_LAUNCH_OK();
   return DWB_OK;
 }

@@ -139,7 +139,9 @@ __global__ void __launch_bounds__(KD_THREADS) kd_loss_kernel(const float* __rest
   const float lseT = f.ms * invT + __logf(f.zT);          // log sum exp(s/T)
   const float lset = has_t ? f.mt * invT + __logf(f.zt) : 0.f;
   if (tid == 0) {
-    row_ce[row] = lse1 - sr[label];
+    // label >= V: CrossEntropyLoss raises (device assert) in the reference; here the row's CE is NaN, so the loss is -- no
+    // out-of-bounds read
+    row_ce[row] = label < V ? lse1 - sr[label] : __int_as_float(0x7fc00000);
     row_kl[row] = has_t ? (f.acc / f.zt - lset + lseT) : 0.f;
   }
   if (dlogits == nullptr) return;

@@ -218,6 +218,16 @@ def kd_loss(student_logits, teacher_logits, labels, vocab, temperature, ce_weigh
     return metrics, dl
 
 
+def scale_bf16_dev(x, scale_dev):
+    """x (contiguous bf16) *= scale_dev (0-d / 1-element fp32 CUDA tensor); free when the scalar is 1."""
+    if not (x.is_contiguous() and x.dtype == BF16 and x.numel() % 8 == 0):
+        raise ValueError("scale_bf16_dev: contiguous bf16 buffer with numel % 8 == 0 required")
+    if scale_dev.dtype != F32 or scale_dev.numel() != 1 or not scale_dev.is_cuda:
+        raise ValueError("scale_bf16_dev: the scale must be a one-element fp32 CUDA tensor")
+    _abi.call("dwb_scale_bf16_dev", _ptr(x), x.numel(), _ptr(scale_dev), _stream())
+    return x
+
+
 def grad_sumsq(g, out):
     _abi.call("dwb_grad_sumsq", _ptr(g), g.numel(), _ptr(out), _stream())
 

@@ -97,6 +97,45 @@ class FusedAdamW(torch.optim.Optimizer):
         self.step_count = 0
         self.grad_scale = 1.0
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=self.flat.data.device)
+        self._bind_state()
+
+    # ---- checkpointing: torch.optim.AdamW's per-parameter layout ------------------------------------------------
+    def _bind_state(self):
+        """Expose the flat moments as `state[p] = {step, exp_avg, exp_avg_sq}` (views), the layout torch.optim.AdamW
+        checkpoints, so `accelerator.save_state` / `load_state` (ref:training/run_distillation.py:1559, :1640) round-trip."""
+        for p, off in self.flat.layout:
+            n = p.numel()
+            self.state[p] = {"step": torch.tensor(float(self.step_count)),
+                             "exp_avg": self.exp_avg[off:off + n].view(p.shape),
+                             "exp_avg_sq": self.exp_avg_sq[off:off + n].view(p.shape)}
+
+    def state_dict(self):
+        for st in self.state.values():
+            st["step"] = torch.tensor(float(self.step_count))
+        sd = super().state_dict()
+        sd["dwb"] = {"step_count": self.step_count, "grad_scale": self.grad_scale, "max_grad_norm": self.max_grad_norm}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        extra = state_dict.get("dwb")
+        super().load_state_dict({k: v for k, v in state_dict.items() if k != "dwb"})
+        steps = set()
+        with torch.no_grad():
+            for p, off in self.flat.layout:
+                st = self.state.get(p)
+                if not st:                       # a checkpoint taken before the first step: moments stay zero
+                    continue
+                n = p.numel()
+                self.exp_avg[off:off + n].view(p.shape).copy_(st["exp_avg"])
+                self.exp_avg_sq[off:off + n].view(p.shape).copy_(st["exp_avg_sq"])
+                steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"FusedAdamW keeps one step count for all parameters; the checkpoint has {sorted(steps)}")
+        self.step_count = steps.pop() if steps else 0
+        if extra:
+            self.step_count = int(extra.get("step_count", self.step_count))
+            self.grad_scale = float(extra.get("grad_scale", self.grad_scale))
+        self._bind_state()
 
     @classmethod
     def for_model(cls, model, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0):

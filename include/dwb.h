@@ -29,6 +29,8 @@ extern "C" {
 
 const char* dwb_last_error(void);
 int dwb_abi_version(void);
+/* Kernel launches issued by the library since the last reset (host-side count; bench.py's `gpu_launches`). */
+int64_t dwb_launch_count(int reset);
 /* 0 iff the current CUDA device is compute capability 10.x (B200).  There is no CPU fallback. */
 int dwb_check_device(void);
 
@@ -77,6 +79,10 @@ int dwb_layernorm_bwd(const void* dy_bf16, const float* x, const float* mean, co
 /* ---- casts / layout -------------------------------------------------------------------------------------------*/
 int dwb_cast_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int rows, int cols, float scale, void* stream);
 int dwb_cast_bf16_to_f32(const void* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, void* stream);
+/* x *= *scale_dev (device scalar; no-op pass when it is 1): applies the upstream gradient of `loss.backward()` /
+ * accelerator.backward(loss) (ref:training/run_distillation.py:1609, which divides by gradient_accumulation_steps) to the
+ * bf16 d loss / d logits produced by dwb_kd_loss.  n % 8 == 0, contiguous. */
+int dwb_scale_bf16_dev(void* x_bf16, int64_t n, const float* scale_dev, void* stream);
 /* Conv1d weight [O,C,3] fp32 -> bf16 [O,3C] with column k*C+c (conv2), and the inverse for its gradient. */
 int dwb_conv_weight_to_kc_bf16(const float* w, void* out_bf16, int O, int C, void* stream);
 int dwb_conv_wgrad_kc_to_ck(const float* g, float* dw, int O, int C, int accumulate, void* stream);

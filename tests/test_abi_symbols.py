@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in _abi.header_symbols() if not hasattr(lib, s)]
     assert not missing, missing
     lib2 = _abi.load()
-    assert _abi.call("dwb_abi_version") == 1
+    assert _abi.call("dwb_abi_version") == 2
     assert isinstance(lib2.dwb_last_error(), bytes)
 
 

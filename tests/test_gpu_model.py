@@ -272,3 +272,107 @@ def test_greedy_generate_follows_the_oracle_argmax():
         m.generate(feats.cuda(), num_beams=4)
     with pytest.raises(NotImplementedError):
         m.generate(feats.cuda(), return_timestamps=True)
+
+
+def _tiny_pair(freeze_encoder=True, lr=1e-3):
+    from distil_whisper_b200.kd import DistillationStep
+    from distil_whisper_b200.optim import FusedAdamW
+    sc, tc = wo.PRESETS["tiny-student"], wo.PRESETS["tiny-teacher"]
+    student = _build(sc, wo.init_state_dict(sc, 11), freeze_encoder=freeze_encoder)
+    teacher = _build(tc, wo.init_state_dict(tc, 23), dtype=torch.bfloat16)
+    step = DistillationStep(student, teacher)
+    return sc, step, FusedAdamW.for_model(student, lr=lr, weight_decay=0.01, max_grad_norm=1.0)
+
+
+@pytest.mark.parametrize("freeze_encoder", [True, False])
+def test_pipelined_trainer_matches_the_eager_loop_from_pinned_host_batches(freeze_encoder):
+    """PipelinedTrainer (graph E | graph D | all-reduce + clip + AdamW on a side stream under the next E) == the reference loop
+    body (ref :1606-1614) issued eagerly, with batches arriving in pinned HOST memory (the bench's e2e path), and with
+    gradient_accumulation_steps = 2 (1/2 folded into the loss kernel, one optimiser step per two micro-batches)."""
+    from distil_whisper_b200.kd import PipelinedTrainer
+    sc, step_e, opt_e = _tiny_pair(freeze_encoder)
+    _, step_p, opt_p = _tiny_pair(freeze_encoder)
+    host = [{k: v.pin_memory() for k, v in wo.synthetic_batch(sc, batch=3, n_tok=12, seed=s).items()} for s in (5, 6, 7, 8, 9, 10)]
+    trainer = PipelinedTrainer(step_p, opt_p, _cuda(host[0]), temperature=2.0, gradient_accumulation_steps=2)
+    assert float(opt_p.flat.grad.abs().sum()) == 0.0
+    assert ("student" in trainer.pre) == freeze_encoder and ("teacher" in trainer.pre) == (not freeze_encoder)
+    for i, hb in enumerate(host):
+        le, _ = step_e.train_step(_cuda(hb), 2.0, loss_scale=0.5)
+        le.backward()
+        lp = trainer.step(hb)
+        assert abs(le.item() - lp.item()) < 5e-5 * abs(le.item()), (i, le.item(), lp.item())
+        if i % 2 == 1:
+            opt_e.all_reduce_gradients()
+            opt_e.step()
+            opt_e.zero_grad()
+    trainer.flush()
+    torch.cuda.synchronize()
+    assert opt_p.step_count == opt_e.step_count == 3
+    assert _rel(opt_p.flat.data, opt_e.flat.data) < 1e-5
+    assert float(opt_p.flat.grad.abs().sum()) == 0.0
+
+
+def test_upstream_gradient_of_backward_is_honoured():
+    """accelerator.backward(loss) divides the loss by gradient_accumulation_steps before .backward() (ref :1607-1609): the
+    gradient handed to _KDStepFn.backward must scale d loss / d logits, not be dropped."""
+    sc, step, opt = _tiny_pair()
+    batch = _cuda(wo.synthetic_batch(sc, batch=3, n_tok=12, seed=5))
+    loss, _ = step.train_step(batch, 2.0)
+    loss.backward()
+    g1 = opt.flat.grad.clone()
+    opt.flat.grad.zero_()
+    loss, _ = step.train_step(batch, 2.0)
+    (loss / 4).backward()
+    assert _rel(opt.flat.grad, g1 / 4) < 1e-2              # dlogits are re-rounded to bf16 after the scale
+    opt.flat.grad.zero_()
+    loss, _ = step.train_step(batch, 2.0, loss_scale=0.25)
+    loss.backward()
+    assert _rel(opt.flat.grad, g1 / 4) < 2e-3
+
+
+def test_fused_adamw_state_dict_round_trip_resumes_identically():
+    """accelerator.save_state / load_state (ref :1559, :1640) go through optimizer.state_dict(): save -> load into a fresh
+    optimiser -> the next steps are bit-identical to the uninterrupted run; the layout is torch.optim.AdamW's."""
+    import io
+    sc, step_a, opt_a = _tiny_pair()
+    _, step_b, opt_b = _tiny_pair()
+    batches = [_cuda(wo.synthetic_batch(sc, batch=3, n_tok=12, seed=s)) for s in (5, 6, 7)]
+
+    def run(step, opt, b):
+        loss, _ = step.train_step(b, 2.0)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+    run(step_a, opt_a, batches[0])
+    run(step_a, opt_a, batches[1])
+    buf = io.BytesIO()
+    torch.save({"opt": opt_a.state_dict(), "model": step_a.student.state_dict()}, buf)
+    buf.seek(0)
+    ck = torch.load(buf)
+    st = ck["opt"]["state"]
+    assert all(set(v) == {"step", "exp_avg", "exp_avg_sq"} for v in st.values()) and len(st) == len(opt_a.flat.layout)
+    step_b.student.load_state_dict(ck["model"])
+    opt_b.load_state_dict(ck["opt"])
+    assert opt_b.step_count == 2
+    run(step_a, opt_a, batches[2])
+    run(step_b, opt_b, batches[2])
+    assert torch.equal(opt_a.exp_avg, opt_b.exp_avg) and torch.equal(opt_a.exp_avg_sq, opt_b.exp_avg_sq)
+    assert _rel(opt_b.flat.data, opt_a.flat.data) < 1e-6
+    # a torch.optim.AdamW over the same parameters accepts the checkpoint (same per-parameter layout)
+    ta = torch.optim.AdamW([{"params": g["params"]} for g in opt_a.param_groups], lr=1e-3)
+    ta.load_state_dict({k: v for k, v in opt_a.state_dict().items() if k != "dwb"})
+
+
+def test_out_of_range_label_or_token_id_poisons_the_loss_instead_of_reading_out_of_bounds():
+    sc, step, opt = _tiny_pair()
+    batch = _cuda(wo.synthetic_batch(sc, batch=3, n_tok=12, seed=5))
+    bad = {k: v.clone() for k, v in batch.items()}
+    bad["labels"][1, 2] = sc.vocab_size + 5
+    loss, _ = step.train_step(bad, 2.0)
+    assert torch.isnan(loss).item()
+    bad = {k: v.clone() for k, v in batch.items()}
+    bad["decoder_input_ids"][0, 1] = sc.vocab_size
+    loss, _ = step.train_step(bad, 2.0)
+    assert torch.isnan(loss).item()
+    loss, _ = step.train_step(batch, 2.0)
+    assert torch.isfinite(loss).item()
