@@ -1,0 +1,258 @@
+// Single-token decoder step for greedy generation (the eval loop's `model.generate`, ref:training/run_distillation.py:1524-1528,
+// and the pseudo-labelling loop, ref:training/run_pseudo_labelling.py:861-927): what HF does with a KV cache
+// (HF:models/whisper/modeling_whisper.py:315-340, EncoderDecoderCache) plus the greedy token pick of
+// HF:generation/utils.py `_sample` (arg-max, finished rows padded, EOS bookkeeping) and the two Whisper logits processors
+// (HF:generation/logits_process.py SuppressTokensLogitsProcessor / SuppressTokensAtBeginLogitsProcessor) as additive biases.
+//
+// Everything position-dependent is read from DEVICE memory (`pos_dev`), so one captured CUDA graph of the whole step is
+// replayed for every token: embedding of seq[:, pos], per layer {LN, QKV GEMM, attention over the cache (this file), ...},
+// LM head, pick -> seq[:, pos + 1], advance.
+//
+// All kernels here are HBM-bound by construction (one query row per (batch, head)): the attention kernel reads every cached
+// K and V row exactly once (2 * len * 128 B per head), which is its algorithmic traffic.
+#include "common.cuh"
+
+namespace dwb {
+
+// ------------------------------------------------------------------------------------------------
+// x[b, :] = E[seq[b, pos]] + P[pos]
+template <typename TE>
+__global__ void embed_decode_kernel(const int64_t* __restrict__ seq, int seq_ld, const int* __restrict__ pos_dev, const TE* __restrict__ E,
+                                    const TE* __restrict__ P, float* __restrict__ x, int d, int vocab) {
+  const int b = blockIdx.x;
+  const int pos = *pos_dev;
+  const int64_t id = seq[(int64_t)b * seq_ld + pos];
+  const bool ok = id >= 0 && id < vocab;
+  for (int c = threadIdx.x; c < d; c += blockDim.x)
+    x[(int64_t)b * d + c] = ok ? (float)E[id * d + c] + (float)P[(int64_t)pos * d + c] : __int_as_float(0x7fc00000);
+}
+
+// ------------------------------------------------------------------------------------------------
+// One query row per (head, batch): o = softmax(scale * q K^T) V over cache rows [0, len).
+//   self-attention (k_new != null): the step's own k / v row is first appended to the cache at row pos, len = pos + 1
+//   cross-attention (k_new == null): len = fixed_len (the encoder positions), the cache is read-only
+// Phase 1: thread t scores keys t, t+128, ... (a K row of one head is 128 B: eight 16 B loads, q in registers)
+// Phase 2: block max / sum of exp2
+// Phase 3: warp w accumulates keys w, w+4, ... ; lane l owns output dims 2l, 2l+1 (a V row of one head = one 128 B request)
+constexpr int AD_THREADS = 128;
+
+__global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restrict__ k_new,
+                                                                 const bf16* __restrict__ v_new, int64_t ld_new, bf16* __restrict__ k_cache,
+                                                                 bf16* __restrict__ v_cache, int64_t ld_cache, int cache_rows,
+                                                                 bf16* __restrict__ o, int64_t ldo, int fixed_len,
+                                                                 const int* __restrict__ pos_dev, float scale_log2) {
+  extern __shared__ float s_p[];                 // [len] scores -> probabilities
+  __shared__ float s_red[AD_THREADS / 32];
+  __shared__ float s_acc[AD_THREADS / 32][64];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int len = fixed_len;
+  bf16* kc = k_cache + (int64_t)b * cache_rows * ld_cache + h * 64;
+  bf16* vc = v_cache + (int64_t)b * cache_rows * ld_cache + h * 64;
+  if (k_new != nullptr) {
+    const int pos = *pos_dev;
+    len = pos + 1;
+    if (tid < 16) {                              // append this step's key / value row (2 x 128 B) to the cache
+      const bf16* src = (tid < 8 ? k_new : v_new) + (int64_t)b * ld_new + h * 64 + (tid & 7) * 8;
+      bf16* dst = (tid < 8 ? kc : vc) + (int64_t)pos * ld_cache + (tid & 7) * 8;
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+    }
+    __syncthreads();
+  }
+  // q * scale * log2(e) in registers
+  float qf[64];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(q + (int64_t)b * ldq + h * 64);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 u = qp[i];
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        qf[i * 8 + j * 2] = f.x * scale_log2;
+        qf[i * 8 + j * 2 + 1] = f.y * scale_log2;
+      }
+    }
+  }
+  float mx = -INFINITY;
+  for (int k = tid; k < len; k += AD_THREADS) {
+    const uint4* kp = reinterpret_cast<const uint4*>(kc + (int64_t)k * ld_cache);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 u = kp[i];
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        s = fmaf(qf[i * 8 + j * 2], f.x, s);
+        s = fmaf(qf[i * 8 + j * 2 + 1], f.y, s);
+      }
+    }
+    s_p[k] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int k = tid; k < len; k += AD_THREADS) {
+    const float e = fast_exp2(s_p[k] - mx);
+    s_p[k] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  const float inv = 1.f / (s_red[0] + s_red[1] + s_red[2] + s_red[3]);
+  float a0 = 0.f, a1 = 0.f;
+  int k = warp;
+  for (; k + 3 * (AD_THREADS / 32) < len; k += 4 * (AD_THREADS / 32)) {     // four independent 128 B requests in flight per warp
+    uint32_t u[4];
+    float pr[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = k + i * (AD_THREADS / 32);
+      u[i] = *reinterpret_cast<const uint32_t*>(vc + (int64_t)kk * ld_cache + 2 * lane);
+      pr[i] = s_p[kk];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack_bf16x2(u[i]);
+      a0 = fmaf(pr[i], f.x, a0);
+      a1 = fmaf(pr[i], f.y, a1);
+    }
+  }
+  for (; k < len; k += AD_THREADS / 32) {
+    const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vc + (int64_t)k * ld_cache + 2 * lane));
+    const float pr = s_p[k];
+    a0 = fmaf(pr, f.x, a0);
+    a1 = fmaf(pr, f.y, a1);
+  }
+  s_acc[warp][2 * lane] = a0;
+  s_acc[warp][2 * lane + 1] = a1;
+  __syncthreads();
+  if (tid < 32) {
+    const float r0 = (s_acc[0][2 * tid] + s_acc[1][2 * tid]) + (s_acc[2][2 * tid] + s_acc[3][2 * tid]);
+    const float r1 = (s_acc[0][2 * tid + 1] + s_acc[1][2 * tid + 1]) + (s_acc[2][2 * tid + 1] + s_acc[3][2 * tid + 1]);
+    *reinterpret_cast<uint32_t*>(o + (int64_t)b * ldo + h * 64 + 2 * tid) = pack_bf16x2(r0 * inv, r1 * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Greedy pick for row b after the step at position pos produced the logits of position pos + 1:
+//   pos + 1 < prompt_len : the next token is the prompt's (already in seq), nothing is written
+//   else next = finished[b] ? pad : argmax_v(logits[b, v] + bias_all[v] + (pos + 1 == begin_pos ? bias_begin[v] : 0));
+//        seq[b, pos + 1] = next; finished[b] |= next == eos          (lowest index wins ties, like torch.argmax)
+constexpr int GP_THREADS = 256;
+__global__ void __launch_bounds__(GP_THREADS) greedy_pick_kernel(const float* __restrict__ logits, int64_t ld, int vocab,
+                                                                 const float* __restrict__ bias_all, const float* __restrict__ bias_begin,
+                                                                 int begin_pos, int64_t* __restrict__ seq, int seq_ld, int prompt_len,
+                                                                 int* __restrict__ finished, int64_t eos, int64_t pad,
+                                                                 const int* __restrict__ pos_dev) {
+  __shared__ float s_v[GP_THREADS / 32];
+  __shared__ int s_i[GP_THREADS / 32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int nxt = *pos_dev + 1;
+  if (nxt < prompt_len || nxt >= seq_ld) return;
+  if (finished[b]) {
+    if (tid == 0) seq[(int64_t)b * seq_ld + nxt] = pad;
+    return;
+  }
+  const float* row = logits + (int64_t)b * ld;
+  const bool at_begin = bias_begin != nullptr && nxt == begin_pos;
+  float best = -INFINITY;
+  int best_i = 0x7fffffff;
+  for (int c = tid; c < vocab; c += GP_THREADS) {
+    float v = row[c];
+    if (bias_all) v += bias_all[c];
+    if (at_begin) v += bias_begin[c];
+    if (v > best) { best = v; best_i = c; }       // strided scan: within a thread indices increase, so '>' keeps the lowest
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+  }
+  if ((tid & 31) == 0) { s_v[tid >> 5] = best; s_i[tid >> 5] = best_i; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < GP_THREADS / 32; ++w)
+      if (s_v[w] > best || (s_v[w] == best && s_i[w] < best_i)) { best = s_v[w]; best_i = s_i[w]; }
+    if (best_i == 0x7fffffff) best_i = 0;          // all -inf / NaN row
+    seq[(int64_t)b * seq_ld + nxt] = best_i;
+    if ((int64_t)best_i == eos) finished[b] = 1;
+  }
+}
+
+// pos += 1; done_at = first position count at which every row had finished (0 while some row is still decoding)
+__global__ void decode_advance_kernel(int* __restrict__ pos_dev, const int* __restrict__ finished, int B, int* __restrict__ done_at) {
+  int all = 1;
+  for (int i = threadIdx.x; i < B; i += 32) all &= finished[i] != 0;
+  all = __all_sync(0xffffffffu, all);
+  if (threadIdx.x == 0) {
+    const int p = *pos_dev + 1;
+    *pos_dev = p;
+    if (all && *done_at == 0) *done_at = p + 1;    // sequences are complete up to and including index p
+  }
+}
+
+}  // namespace dwb
+
+using namespace dwb;
+
+extern "C" int dwb_embed_decode(const int64_t* seq, int seq_ld, const int* pos_dev, const void* E, const void* P, int table_is_f32,
+                                float* x, int B, int d, int vocab, void* stream) {
+  DWB_CHECK_ARG(seq && pos_dev && E && P && x && B > 0 && d > 0 && seq_ld > 0, "dwb_embed_decode: bad args");
+  if (table_is_f32)
+    embed_decode_kernel<float><<<B, 256, 0, (cudaStream_t)stream>>>(seq, seq_ld, pos_dev, (const float*)E, (const float*)P, x, d, vocab);
+  else
+    embed_decode_kernel<bf16><<<B, 256, 0, (cudaStream_t)stream>>>(seq, seq_ld, pos_dev, (const bf16*)E, (const bf16*)P, x, d, vocab);
+  DWB_LAUNCH_OK();
+  return DWB_OK;
+}
+
+extern "C" int dwb_attention_decode(const void* q, int64_t ldq, const void* k_new, const void* v_new, int64_t ld_new, void* k_cache,
+                                    void* v_cache, int64_t ld_cache, int cache_rows, void* o, int64_t ldo, int B, int H, int head_dim,
+                                    int fixed_len, const int* pos_dev, float scale, void* stream) {
+  DWB_CHECK_ARG(head_dim == 64, "dwb_attention_decode: head_dim %d unsupported (Whisper uses 64)", head_dim);
+  DWB_CHECK_ARG(q && k_cache && v_cache && o && B > 0 && H > 0 && cache_rows > 0, "dwb_attention_decode: bad args");
+  DWB_CHECK_ARG((k_new == nullptr) == (v_new == nullptr), "dwb_attention_decode: k_new and v_new go together");
+  DWB_CHECK_ARG(k_new ? pos_dev != nullptr : (fixed_len > 0 && fixed_len <= cache_rows), "dwb_attention_decode: need pos_dev (append) or 0 < fixed_len <= cache_rows");
+  DWB_CHECK_ARG((ldq % 8) == 0 && (ld_cache % 8) == 0 && (ldo % 2) == 0 && (k_new == nullptr || (ld_new % 8) == 0),
+                "dwb_attention_decode: row pitches must keep 16 B alignment");
+  const size_t smem = (size_t)cache_rows * sizeof(float);
+  DWB_CHECK_ARG(smem <= 200 * 1024, "dwb_attention_decode: %d cache rows exceed the shared-memory score buffer", cache_rows);
+  static size_t smem_set = 48 * 1024;
+  if (smem > smem_set) {
+    DWB_CUDA_OK(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  attn_decode_kernel<<<dim3(H, B), AD_THREADS, smem, (cudaStream_t)stream>>>(
+      (const bf16*)q, ldq, (const bf16*)k_new, (const bf16*)v_new, ld_new, (bf16*)k_cache, (bf16*)v_cache, ld_cache, cache_rows, (bf16*)o, ldo,
+      fixed_len, pos_dev, scale * 1.4426950408889634f);
+  DWB_LAUNCH_OK();
+  return DWB_OK;
+}
+
+extern "C" int dwb_greedy_pick(const float* logits, int64_t ld, int vocab, const float* bias_all, const float* bias_begin, int begin_pos,
+                               int64_t* seq, int seq_ld, int prompt_len, int* finished, int64_t eos, int64_t pad, const int* pos_dev, int B,
+                               void* stream) {
+  DWB_CHECK_ARG(logits && seq && finished && pos_dev && B > 0 && vocab > 0 && ld >= vocab && prompt_len >= 1 && seq_ld >= prompt_len,
+                "dwb_greedy_pick: bad args");
+  greedy_pick_kernel<<<B, GP_THREADS, 0, (cudaStream_t)stream>>>(logits, ld, vocab, bias_all, bias_begin, begin_pos, seq, seq_ld, prompt_len,
+                                                                 finished, eos, pad, pos_dev);
+  DWB_LAUNCH_OK();
+  return DWB_OK;
+}
+
+extern "C" int dwb_decode_advance(int* pos_dev, const int* finished, int B, int* done_at, void* stream) {
+  DWB_CHECK_ARG(pos_dev && finished && done_at && B > 0, "dwb_decode_advance: bad args");
+  decode_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pos_dev, finished, B, done_at);
+  DWB_LAUNCH_OK();
+  return DWB_OK;
+}

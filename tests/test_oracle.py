@@ -87,3 +87,61 @@ def test_logmel_matches_hf_golden(golden_dir, n_mels):
     np.testing.assert_allclose(out.mean(axis=2), g["row_mean"], atol=2e-6)
     np.testing.assert_allclose(out.reshape(3, -1).max(axis=1), g["utt_max"], atol=2e-5)
     np.testing.assert_allclose(out.reshape(3, -1).min(axis=1), g["utt_min"], atol=2e-5)
+
+
+# ---- greedy generation (eval / pseudo-labelling decode) -----------------------------------------------------------------
+GEN_MULTI = dict(decoder_start_token_id=501, eos_token_id=502, pad_token_id=500, bos_token_id=502,
+                 suppress_tokens=[1, 2, 7, 8, 9, 220], begin_suppress_tokens=[220, 502], is_multilingual=True,
+                 lang_to_id={"<|en|>": 503, "<|fr|>": 504, "<|de|>": 505}, task_to_id={"transcribe": 506, "translate": 507},
+                 no_timestamps_token_id=508)
+GEN_EN = dict(decoder_start_token_id=501, eos_token_id=502, pad_token_id=500, bos_token_id=502, is_multilingual=False,
+              no_timestamps_token_id=508, suppress_tokens=None, begin_suppress_tokens=None)
+GEN_CASES = {"A": (GEN_MULTI, dict(language="fr", task="transcribe", max_new_tokens=10)),
+             "B": (GEN_MULTI, dict(max_length=12)),
+             "C": (GEN_EN, dict(max_new_tokens=6))}
+
+
+def test_oracle_greedy_generate_reproduces_hf_golden(golden_dir):
+    """HF's own initial-token logic + suppress processors + greedy search (oracle/gen_golden.py:hf_greedy) on the tiny model:
+    the oracle restatement must emit the same token ids, row for row, including EOS / pad bookkeeping and early stop."""
+    import torch
+    from oracle import whisper_oracle as wo
+    g = np.load(os.path.join(golden_dir, "generate_tiny.npz"))
+    sc = wo.PRESETS["tiny-student"]
+    sd = wo.init_state_dict(sc, int(g["model_seed"]), std=float(g["model_std"]))
+    for name, (cfg, kw) in GEN_CASES.items():
+        feats, init, seq = torch.from_numpy(g[f"{name}_feats"]), torch.from_numpy(g[f"{name}_init"]), g[f"{name}_seq"]
+        limit = kw["max_length"] if "max_length" in kw else init.shape[1] + kw["max_new_tokens"]
+        out = wo.greedy_generate(sd, sc, feats, init, int(g[f"{name}_eos"]), cfg["pad_token_id"], limit, cfg.get("suppress_tokens"),
+                                 [int(t) for t in g[f"{name}_begin_suppress"]])
+        assert out.shape == seq.shape and (out.numpy() == seq).all(), (name, out, seq)
+        assert float(g[f"{name}_min_rel_margin"].min()) > 0.02       # the fixture rows were chosen for decisive arg-maxima
+
+
+def test_initial_tokens_follow_hf_retrieve_init_tokens(golden_dir):
+    """Host logic of distil_whisper_b200.generation.initial_tokens == HF `_retrieve_init_tokens` (golden `*_init`) for: forced
+    language + task, language detection without a task, an English-only config; plus the error cases HF raises on."""
+    import types
+
+    import pytest
+    import torch
+    from distil_whisper_b200 import generation
+    g = np.load(os.path.join(golden_dir, "generate_tiny.npz"))
+    model = types.SimpleNamespace(config=types.SimpleNamespace(decoder_start_token_id=501, forced_decoder_ids=None))
+    a = generation.initial_tokens(model, GEN_MULTI, "fr", "transcribe", False, detect=None)
+    assert a == [g["A_init"][0].tolist()]
+    assert generation.initial_tokens(model, GEN_MULTI, "french", "translate", False, None) == [[501, 504, 507, 508]]
+    assert generation.initial_tokens(model, GEN_MULTI, "<|de|>", None, False, None) == [[501, 505, 506, 508]]
+    assert generation.initial_tokens(model, GEN_MULTI, ["en", "de"], None, True, None) == [[501, 503, 506], [501, 505, 506]]
+    det = torch.as_tensor(g["B_init"][:, 1])
+    b = generation.initial_tokens(model, GEN_MULTI, None, None, False, detect=lambda: det)
+    assert b == g["B_init"].tolist()
+    assert generation.initial_tokens(model, GEN_EN, None, None, False, None) == [g["C_init"][0].tolist()]
+    forced = dict(GEN_MULTI, forced_decoder_ids=[[1, 504], [2, 507], [3, 508]])
+    assert generation.initial_tokens(model, forced, None, None, False, None) == [[501, 504, 507, 508]]
+    with pytest.raises(ValueError):
+        generation.initial_tokens(model, GEN_EN, "en", None, False, None)          # English-only model + language
+    with pytest.raises(ValueError):
+        generation.initial_tokens(model, GEN_MULTI, "xx", None, False, None)       # unknown language
+    with pytest.raises(ValueError):
+        generation.initial_tokens(model, GEN_MULTI, "en", "summarise", False, None)
