@@ -351,6 +351,31 @@ __global__ void __launch_bounds__(256) scale_bf16_dev_kernel(bf16* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Label side of DataCollatorSpeechSeq2SeqWithPadding (ref:training/run_distillation.py:460-476) on the device:
+//   tokens [B, L+1] (padded token ids), lengths [B]  ->  decoder_input_ids = tokens[:, :-1],
+//   labels = tokens[:, 1:] with -100 on padding (t + 1 >= length) and on the prompt: everything before, and including, the
+//   first <|startoftranscript|> found at a label index > 0 (torch.argmax of the boolean row returns the first hit, 0 if none).
+__global__ void __launch_bounds__(128) collate_labels_kernel(const int64_t* __restrict__ tokens, const int* __restrict__ lengths, int L1,
+                                                             int64_t sot, int64_t* __restrict__ dec_in, int64_t* __restrict__ labels) {
+  __shared__ int s_first;
+  const int b = blockIdx.x, L = L1 - 1, len = lengths[b];
+  const int64_t* row = tokens + (int64_t)b * L1;
+  if (threadIdx.x == 0) s_first = 0x7fffffff;
+  __syncthreads();
+  int first = 0x7fffffff;
+  for (int t = threadIdx.x; t < L; t += blockDim.x)
+    if (t + 1 < len && row[t + 1] == sot) { first = t; break; }        // per-thread indices increase: the first hit is its smallest
+  if (first != 0x7fffffff) atomicMin(&s_first, first);
+  __syncthreads();
+  int bos = s_first == 0x7fffffff ? 0 : s_first;
+  if (bos > 0) bos += 1;
+  for (int t = threadIdx.x; t < L; t += blockDim.x) {
+    dec_in[(int64_t)b * L + t] = row[t];
+    labels[(int64_t)b * L + t] = (t + 1 < len && t >= bos) ? row[t + 1] : -100;
+  }
+}
+
 static inline int grid_for(int64_t work_items, int threads) {
   int64_t g = ceil_div64(work_items, threads);
   const int64_t cap = (int64_t)kNumSMs * 16;
@@ -412,6 +437,13 @@ extern "C" int dwb_cast_f32_to_bf16(const float* src, int64_t lds, void* dst, in
                 "dwb_cast_f32_to_bf16: bad shape/alignment rows=%d cols=%d", rows, cols);
   cast_f32_bf16_kernel<<<grid_for((int64_t)rows * cols / 4, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, (bf16*)dst, ldd, rows, cols,
                                                                                                   scale);
+  DWB_LAUNCH_OK();
+  return DWB_OK;
+}
+extern "C" int dwb_collate_labels(const int64_t* tokens, const int* lengths, int B, int L1, int64_t decoder_start_token_id,
+                                  int64_t* decoder_input_ids, int64_t* labels, void* stream) {
+  DWB_CHECK_ARG(tokens && lengths && decoder_input_ids && labels && B > 0 && L1 >= 2, "dwb_collate_labels: bad args");
+  collate_labels_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(tokens, lengths, L1, decoder_start_token_id, decoder_input_ids, labels);
   DWB_LAUNCH_OK();
   return DWB_OK;
 }

@@ -19,6 +19,24 @@ BF16, F32 = torch.bfloat16, torch.float32
 
 
 # =================================================================================================================
+# tracing: NVTX ranges per phase of the step -- visible in nsys / ncu --nvtx timelines, free otherwise
+class nvtx_range:
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        self.on = torch.cuda.is_available()
+        if self.on:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
+# =================================================================================================================
 # parameter shadows
 _PARAM_EPOCH = [0]
 
@@ -553,15 +571,18 @@ def run_encoder(model, input_features, enc_in, save=False):
         return e.contiguous(), e.shape[0] // enc_in.shape[0], None
     if input_features is None:
         raise ValueError("input_features or encoder_outputs are required")
-    out, ectx = encoder_forward(state_of(model.model.encoder), input_features, save=save)
+    with nvtx_range("dwb.encoder_forward"):
+        out, ectx = encoder_forward(state_of(model.model.encoder), input_features, save=save)
     return out, cfg.max_source_positions, ectx
 
 
 def backward_through_model(model, dctx, ectx, dlogits_bf16):
     """Decoder (+ encoder when ectx is given) backward from the bf16 logits gradient; gradients land in .grad."""
-    denc = decoder_backward(state_of(model.model.decoder), dctx, dlogits_bf16, want_denc=ectx is not None)
+    with nvtx_range("dwb.decoder_backward"):
+        denc = decoder_backward(state_of(model.model.decoder), dctx, dlogits_bf16, want_denc=ectx is not None)
     if ectx is not None:
-        encoder_backward(state_of(model.model.encoder), ectx, ops.cast_f32_to_bf16(denc))
+        with nvtx_range("dwb.encoder_backward"):
+            encoder_backward(state_of(model.model.encoder), ectx, ops.cast_f32_to_bf16(denc))
 
 
 class ModelForwardFn(torch.autograd.Function):

@@ -64,6 +64,32 @@ class WhisperFeatureExtractorB200:
         self.mel_filters = slaney_mel_filter_bank(1 + n_fft // 2, feature_size, 0.0, 8000.0, sampling_rate)
         self._plan = None
 
+    # -- (de)serialisation: ref:training/run_distillation.py:1071, :1641, :1754, :1783 call feature_extractor.save_pretrained ----
+    def to_dict(self):
+        return {"feature_extractor_type": "WhisperFeatureExtractor", "processor_class": "WhisperProcessor",
+                "feature_size": self.feature_size, "sampling_rate": self.sampling_rate, "hop_length": self.hop_length,
+                "chunk_length": self.chunk_length, "n_fft": self.n_fft, "padding_value": self.padding_value, "padding_side": "right",
+                "n_samples": self.n_samples, "nb_max_frames": self.nb_max_frames, "return_attention_mask": False}
+
+    def save_pretrained(self, save_directory, **kwargs):
+        """Writes preprocessor_config.json in transformers' layout (loadable by WhisperFeatureExtractor.from_pretrained)."""
+        import json
+        import os
+        os.makedirs(save_directory, exist_ok=True)
+        path = os.path.join(save_directory, "preprocessor_config.json")
+        with open(path, "w") as f:
+            json.dump(self.to_dict(), f, indent=2, sort_keys=True)
+        return [path]
+
+    @classmethod
+    def from_pretrained(cls, directory, **kwargs):
+        import json
+        import os
+        with open(os.path.join(directory, "preprocessor_config.json")) as f:
+            cfg = json.load(f)
+        keys = ("feature_size", "sampling_rate", "hop_length", "chunk_length", "n_fft", "padding_value")
+        return cls(**{k: cfg[k] for k in keys if k in cfg})
+
     # -- device plan ------------------------------------------------------------------------------------------
     def _get_plan(self):
         if self._plan is None:

@@ -34,8 +34,9 @@ class _KDStepFn(torch.autograd.Function):
         else:
             enc_s, S, ectx = engine.run_encoder(student, feats, None, save=train)
         sst = engine.state_of(student.model.decoder)
-        hf_s, dctx = engine.decoder_forward(sst, dec_in, enc_s, B, S, save=train)
-        logits_s = engine.lm_head(sst, hf_s)
+        with engine.nvtx_range("dwb.student_decoder_forward"):
+            hf_s, dctx = engine.decoder_forward(sst, dec_in, enc_s, B, S, save=train)
+            logits_s = engine.lm_head(sst, hf_s)
         # ---- teacher, no grad (ref :1473-1481)
         tst = engine.state_of(teacher.model.decoder)
         if step.share_hidden_states:
@@ -46,11 +47,13 @@ class _KDStepFn(torch.autograd.Function):
         else:
             t_in = dec_in
             enc_t = pre["teacher"][0]
-        hf_t, _ = engine.decoder_forward(tst, t_in, enc_t, B, S, save=False)
-        logits_t = engine.lm_head(tst, hf_t)
+        with engine.nvtx_range("dwb.teacher_decoder_forward"):
+            hf_t, _ = engine.decoder_forward(tst, t_in, enc_t, B, S, save=False)
+            logits_t = engine.lm_head(tst, hf_t)
         # ---- fused loss head (ref :1484-1493)
-        metrics, dl = ops.kd_loss(logits_s, logits_t, labels, V, temperature, 0.8 * loss_scale, step.kl_weight * loss_scale,
-                                  want_grad=train)
+        with engine.nvtx_range("dwb.kd_loss"):
+            metrics, dl = ops.kd_loss(logits_s, logits_t, labels, V, temperature, 0.8 * loss_scale, step.kl_weight * loss_scale,
+                                      want_grad=train)
         if train:
             ctx.step, ctx.dctx, ctx.ectx, ctx.dl = step, dctx, ectx, dl
         step.last_student_logits = logits_s.view(B, T, -1)[:, :, :V] if step.keep_logits else None
@@ -248,8 +251,10 @@ class PipelinedTrainer:
             self.bwd_done.record(main)
             with torch.cuda.stream(self.side):
                 self.side.wait_event(self.bwd_done)
-                self.opt.all_reduce_gradients(self.group)
-                self.opt.step()
+                with engine.nvtx_range("dwb.grad_all_reduce"):
+                    self.opt.all_reduce_gradients(self.group)
+                with engine.nvtx_range("dwb.clip_adamw"):
+                    self.opt.step()
                 self.tail_done.record(self.side)
             self._tail_pending = True
         return self.loss

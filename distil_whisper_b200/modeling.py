@@ -225,17 +225,59 @@ class DistilWhisperB200ForConditionalGeneration(nn.Module):
         m.generation_config = getattr(hf_model, "generation_config", None)
         return m.to(dtype) if dtype is not None else m
 
-    def save_pretrained(self, save_directory, **kwargs):
+    def save_pretrained(self, save_directory, safe_serialization=True, **kwargs):
+        """config.json + model.safetensors (or pytorch_model.bin) with Hugging Face's parameter names, loadable by
+        transformers.WhisperForConditionalGeneration.from_pretrained and by from_pretrained below (ref:training/
+        run_distillation.py:1643-1652, :1754-1760 save the student this way through accelerate)."""
         import json
         import os
         os.makedirs(save_directory, exist_ok=True)
-        sd = {k: v.detach().cpu() for k, v in self.state_dict().items() if k != "proj_out.weight"}
-        torch.save(sd, os.path.join(save_directory, "pytorch_model.bin"))
+        sd = {k: v.detach().to("cpu").contiguous() for k, v in self.state_dict().items() if k != "proj_out.weight"}
+        if safe_serialization:
+            from safetensors.torch import save_file
+            save_file(sd, os.path.join(save_directory, "model.safetensors"), metadata={"format": "pt"})
+        else:
+            torch.save(sd, os.path.join(save_directory, "pytorch_model.bin"))
         with open(os.path.join(save_directory, "config.json"), "w") as f:
             json.dump({"model_type": "whisper", "architectures": ["WhisperForConditionalGeneration"], **self.config.to_dict()}, f, indent=2)
+        gen = self.generation_config
+        if gen is not None:
+            gd = gen if isinstance(gen, dict) else (gen.to_dict() if hasattr(gen, "to_dict") else dict(vars(gen)))
+            with open(os.path.join(save_directory, "generation_config.json"), "w") as f:
+                json.dump(gd, f, indent=2, default=str)
+
+    @classmethod
+    def from_pretrained(cls, directory, torch_dtype=None, device=None, **kwargs):
+        """Load a directory written by save_pretrained above or by transformers (config.json + model.safetensors /
+        pytorch_model.bin, single shard).  Mirrors the call at ref:training/run_distillation.py:986-1004 for local paths."""
+        import json
+        import os
+        with open(os.path.join(directory, "config.json")) as f:
+            model = cls(json.load(f))
+        st, pt = os.path.join(directory, "model.safetensors"), os.path.join(directory, "pytorch_model.bin")
+        if os.path.exists(st):
+            from safetensors.torch import load_file
+            sd = load_file(st)
+        elif os.path.exists(pt):
+            sd = torch.load(pt, map_location="cpu")
+        else:
+            raise FileNotFoundError(f"no model.safetensors / pytorch_model.bin in {directory} (sharded checkpoints are not supported)")
+        model.load_hf_state_dict(sd)
+        gpath = os.path.join(directory, "generation_config.json")
+        if os.path.exists(gpath):
+            with open(gpath) as f:
+                model.generation_config = json.load(f)
+        if torch_dtype is not None:
+            model = model.to(torch_dtype)
+        return model.to(device) if device is not None else model
 
     def gradient_checkpointing_enable(self, *a, **k):
-        # activations of the trainable part fit in 180 GB at the reference batch size; nothing to recompute
+        """ref:training/run_distillation.py:1012-1013 calls this when --gradient_checkpointing is set.  This implementation
+        keeps every activation of the trainable part resident (they fit in 180 GB at the reference batch size)
+        and has no recomputation schedule: the request is acknowledged with a warning, never silently."""
+        import warnings
+        warnings.warn("distil_whisper_b200: gradient checkpointing is not implemented (activations stay resident in HBM); "
+                      "continuing without recomputation", stacklevel=2)
         self.model.encoder.gradient_checkpointing = False
         self.model.decoder.gradient_checkpointing = False
 

@@ -216,6 +216,16 @@ def decode_advance(pos_dev, finished, done_at):
     _abi.call("dwb_decode_advance", _ptr(pos_dev), _ptr(finished), finished.numel(), _ptr(done_at), _stream())
 
 
+def collate_labels(tokens, lengths, decoder_start_token_id):
+    """tokens int64 [B, L+1] (padded), lengths int32 [B] (CUDA) -> (decoder_input_ids, labels) int64 [B, L]."""
+    assert tokens.dtype == torch.int64 and tokens.is_contiguous() and lengths.dtype == torch.int32 and tokens.is_cuda and lengths.is_cuda
+    B, L1 = tokens.shape
+    dec_in = torch.empty((B, L1 - 1), dtype=torch.int64, device=tokens.device)
+    labels = torch.empty((B, L1 - 1), dtype=torch.int64, device=tokens.device)
+    _abi.call("dwb_collate_labels", _ptr(tokens), _ptr(lengths), B, L1, int(decoder_start_token_id), _ptr(dec_in), _ptr(labels), _stream())
+    return dec_in, labels
+
+
 def colsum(m, out=None, accumulate=False):
     _check2d(m, BF16, "colsum")
     if out is None:

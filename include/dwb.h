@@ -122,6 +122,12 @@ int dwb_greedy_pick(const float* logits, int64_t ld, int vocab, const float* bia
                     int seq_ld, int prompt_len, int* finished, int64_t eos, int64_t pad, const int* pos_dev, int B, void* stream);
 int dwb_decode_advance(int* pos_dev, const int* finished, int B, int* done_at, void* stream);
 
+/* ---- label side of the data collator: ref:training/run_distillation.py:460-476 --------------------------------------
+ * tokens [B, L1] int64 (padded), lengths [B] int32 -> decoder_input_ids [B, L1-1] = tokens[:, :-1]; labels [B, L1-1] =
+ * tokens[:, 1:] with -100 on padding and on the prompt up to and including <|startoftranscript|>. */
+int dwb_collate_labels(const int64_t* tokens, const int* lengths, int B, int L1, int64_t decoder_start_token_id,
+                       int64_t* decoder_input_ids, int64_t* labels, void* stream);
+
 /* ---- small reductions / activations ---------------------------------------------------------------------------*/
 int dwb_colsum_bf16(const void* m_bf16, int64_t ld, float* out, int rows, int cols, int accumulate, void* stream); /* bias grads */
 int dwb_gelu_bwd(const void* da, const void* h, void* dh, int64_t n, void* stream);

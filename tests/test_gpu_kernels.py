@@ -1,6 +1,8 @@
 """Per-kernel parity of the non-GEMM C-ABI entry points against plain PyTorch fp32 on the GPU."""
 import math
 
+import numpy as np
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -352,3 +354,39 @@ def test_decode_attention_and_greedy_pick_against_torch():
     finished.fill_(1)
     ops.decode_advance(p, finished, done)
     assert int(done) == int(p) + 1
+
+
+def test_device_collator_matches_reference_collator_semantics():
+    """dwb_collate_labels + DataCollatorSpeechSeq2SeqWithPaddingB200 against the oracle's restatement of the reference collator
+    (ref:training/run_distillation.py:438-478): shift, -100 on padding, -100 on the prompt up to and including SOT; raw audio
+    in -> log-mel computed on the device equals the extractor's own output."""
+    from distil_whisper_b200.data import DataCollatorSpeechSeq2SeqWithPaddingB200
+    from distil_whisper_b200.feature_extraction import WhisperFeatureExtractorB200
+    from oracle import logmel_oracle as lo
+    from oracle import whisper_oracle as wo
+    sot, prev, pad = 501, 502, 500
+    rows = [[sot, 7, 8, 9, 10],                              # plain row
+            [prev, 3, 4, sot, 11, 12, 13],                   # prompted row: -100 up to and including SOT
+            [sot, 5],                                        # short row
+            [prev, 1, sot, 2, sot, 3, 4, 5, 6, 7, 8, 9]]     # a second SOT later in the row: only the first counts
+    wav = lo.synthetic_waveforms(len(rows), seed=3, ragged=True)
+    fe = WhisperFeatureExtractorB200(80)
+    coll = DataCollatorSpeechSeq2SeqWithPaddingB200(None, sot, prev, max_target_length=14, pad_token_id=pad, feature_extractor=fe)
+    feats_in = [{"input_values": wav[i][: 480000 - 1000 * i], "labels": r} for i, r in enumerate(rows)]
+    batch = coll(feats_in)
+    dec_ref, lab_ref = wo.collate_labels(rows, pad, sot, max_len=14)
+    assert batch["decoder_input_ids"].is_cuda and torch.equal(batch["decoder_input_ids"].cpu(), dec_ref)
+    assert torch.equal(batch["labels"].cpu(), lab_ref), (batch["labels"].cpu(), lab_ref)
+    assert (lab_ref[1, :4] == -100).all() and lab_ref[1, 4] == 12 and lab_ref[3, 2] == 2     # the fixture exercises the prompt mask
+    want = fe.extract_device(torch.from_numpy(fe.pad_or_trim([f["input_values"] for f in feats_in])).cuda())
+    assert batch["input_features"].shape == (4, 80, 3000) and torch.equal(batch["input_features"], want)
+    ref0 = lo.log_mel(fe.pad_or_trim([feats_in[1]["input_values"]]), 80)
+    assert np.abs(batch["input_features"][1].cpu().numpy() - ref0[0]).max() < 2e-4
+    # precomputed features (the reference's dataset layout) pass through unchanged
+    b2 = coll([{"input_features": want[i].cpu().numpy(), "labels": r} for i, r in enumerate(rows)])
+    assert torch.equal(b2["input_features"], want) and torch.equal(b2["labels"].cpu(), lab_ref)
+    # longest padding
+    coll2 = DataCollatorSpeechSeq2SeqWithPaddingB200(None, sot, prev, target_padding="longest", pad_token_id=pad, feature_extractor=fe)
+    b3 = coll2([{"input_features": want[i], "labels": r} for i, r in enumerate(rows)])
+    d3, l3 = wo.collate_labels(rows, pad, sot)
+    assert torch.equal(b3["labels"].cpu(), l3) and torch.equal(b3["decoder_input_ids"].cpu(), d3)

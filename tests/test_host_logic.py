@@ -109,3 +109,55 @@ def test_generate_rejects_unsupported_decoding_modes_before_touching_the_device(
     for kw in (dict(num_beams=4), dict(do_sample=True), dict(return_timestamps=True), dict(forced_decoder_ids=[(1, 2)])):
         with pytest.raises(NotImplementedError):
             m.generate(feats, **kw)
+
+
+def test_pad_label_rows_matches_tokenizer_pad_semantics():
+    """Host half of the device collator (distil_whisper_b200/data.py): right padding to max_target_length / longest, lengths."""
+    import pytest
+    from distil_whisper_b200.data import pad_label_rows
+    rows = [[5, 6, 7, 8], [9], [1, 2]]
+    t, l = pad_label_rows(rows, 99, 6, "max_length")
+    assert t.tolist() == [[5, 6, 7, 8, 99, 99], [9, 99, 99, 99, 99, 99], [1, 2, 99, 99, 99, 99]] and l.tolist() == [4, 1, 2]
+    t, l = pad_label_rows(rows, 99, None, "longest")
+    assert t.shape == (3, 4) and t[1].tolist() == [9, 99, 99, 99]
+    with pytest.raises(ValueError):
+        pad_label_rows(rows, 99, 3, "max_length")
+    with pytest.raises(ValueError):
+        pad_label_rows(rows, 99, None, "max_length")
+
+
+def test_save_pretrained_round_trips_and_is_hf_loadable(tmp_path):
+    """Model: config.json + model.safetensors with HF names -> from_pretrained (ours) and transformers' own loader agree.
+    Feature extractor: preprocessor_config.json loadable by transformers.WhisperFeatureExtractor (ref :1071, :1641, :1754)."""
+    import pytest
+    import torch
+    from distil_whisper_b200.feature_extraction import WhisperFeatureExtractorB200
+    from distil_whisper_b200.modeling import DistilWhisperB200ForConditionalGeneration
+    from oracle import whisper_oracle as wo
+    sc = wo.PRESETS["tiny-student"]
+    m = DistilWhisperB200ForConditionalGeneration(sc.to_dict())
+    m.load_hf_state_dict(wo.init_state_dict(sc, 3))
+    m.generation_config = {"decoder_start_token_id": 501, "lang_to_id": {"<|en|>": 503}}
+    d = tmp_path / "ckpt"
+    m.save_pretrained(str(d))
+    assert (d / "model.safetensors").exists() and (d / "config.json").exists()
+    m2 = DistilWhisperB200ForConditionalGeneration.from_pretrained(str(d))
+    for (k, a), (k2, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert k == k2 and torch.equal(a, b), k
+    assert m2.generation_config["lang_to_id"] == {"<|en|>": 503}
+    assert m2.proj_out.weight.data_ptr() == m2.model.decoder.embed_tokens.weight.data_ptr()
+    transformers = pytest.importorskip("transformers")
+    hf = transformers.WhisperForConditionalGeneration.from_pretrained(str(d))
+    hsd = hf.state_dict()
+    for k, v in m.state_dict().items():
+        assert torch.equal(hsd[k], v), k
+    m.save_pretrained(str(tmp_path / "bin"), safe_serialization=False)
+    m3 = DistilWhisperB200ForConditionalGeneration.from_pretrained(str(tmp_path / "bin"), torch_dtype=torch.bfloat16)
+    assert m3.model.decoder.layers[0].fc1.weight.dtype == torch.bfloat16
+    fe = WhisperFeatureExtractorB200(128)
+    fe.save_pretrained(str(d))
+    hfe = transformers.WhisperFeatureExtractor.from_pretrained(str(d))
+    assert hfe.feature_size == 128 and hfe.n_fft == 400 and hfe.hop_length == 160 and hfe.chunk_length == 30
+    assert WhisperFeatureExtractorB200.from_pretrained(str(d)).feature_size == 128
+    with pytest.warns(UserWarning):
+        m.gradient_checkpointing_enable()
