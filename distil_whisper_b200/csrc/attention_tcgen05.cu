@@ -11,6 +11,8 @@
 //
 // Replaces F.scaled_dot_product_attention (HF:integrations/sdpa_attention.py:40-104) for
 // HF:models/whisper/modeling_whisper.py:342-352 in the encoder (is_causal False), same contract as dwb_attention_fwd.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dwb {
@@ -25,11 +27,31 @@ constexpr int TA_BAR_BYTES = 112;
 constexpr int TA_SMEM = 115712;
 static_assert(TA_TILES_BYTES + TA_BAR_BYTES + 896 <= TA_SMEM, "smem budget");
 constexpr int TA_TMEM_COLS = 256;
+constexpr int TA_DEFAULT_VARIANT = 0;   // np8 + 10 * defer (see dwb_attention_fwd_tc)
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
+}
+
+// 2^x for a pair of scores on the FMA / ALU pipes instead of the MUFU (the XU pipe, 16 exp2 per clock per SM, is what bounds
+// this kernel at head_dim 64): Cody-Waite split x = n + f with n = round(x) taken from the float's own mantissa
+// (x + 1.5 * 2^23), 2^f by a degree-3 minimax polynomial on [-0.5, 0.5] (max relative error 7.5e-5, fifty times below the bf16
+// rounding P receives next), and n added into the exponent field.  x is clamped to [-126, 126]: a masked score (-inf) becomes
+// 2^-126 (nothing), an overflowing one 2^126, which the tile-sum test of the lazy rescale still catches.
+__device__ __forceinline__ float2 poly_exp2_pair(float2 x) {
+  x.x = fminf(fmaxf(x.x, -126.f), 126.f);
+  x.y = fminf(fmaxf(x.y, -126.f), 126.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f), neg_magic = make_float2(-12582912.f, -12582912.f);
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(t, neg_magic);
+  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
+  float2 q = __ffma2_rn(make_float2(0.055171459913253784f, 0.055171459913253784f), f, make_float2(0.2426108568906784f, 0.2426108568906784f));
+  q = __ffma2_rn(q, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  q = __ffma2_rn(q, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
+  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
 }
 
 struct TcAttnParams {
@@ -39,6 +61,11 @@ struct TcAttnParams {
   float* lse;           // [B, H, Sq] or null
 };
 
+// NP8: of every 8 score pairs, NP8 take the polynomial exp2 (spread evenly through the unrolled loop so that FMA-pipe chains
+// fill the issue slots between MUFU issues); 0 = all MUFU.
+// DEFER: the wait for "P V of the previous tile has consumed P" is taken after the first 64 exponentials of the tile are in
+// registers instead of before the first one, so that the previous tile's P V (and its completion signalling) runs under them.
+template <int NP8, bool DEFER>
 __global__ void __launch_bounds__(TA_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
@@ -212,10 +239,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           for (int i = 0; i < 64; i += 2) {
             const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[c * 64 + i]), __uint_as_float(v[c * 64 + i + 1])), sc2, nm2);
             float2 e;
-            e.x = fast_exp2(x.x);
-            e.y = fast_exp2(x.y);
+            if ((((i >> 1) * NP8) & 7) < NP8) {
+              e = poly_exp2_pair(x);
+            } else {
+              e.x = fast_exp2(x.x);
+              e.y = fast_exp2(x.y);
+            }
             ls[(i >> 1) & 3] = __fadd2_rn(ls[(i >> 1) & 3], e);
             pk[i >> 1] = pack_bf16x2(e.x, e.y);
+          }
+          if (DEFER && c == 0) {
+            mbar_wait(p_empty, (j & 1) ^ 1);                // P V of the previous tile has consumed P (and updated O)
+            tc_fence_after();
           }
           tmem_st_32x32(t_p + c * 32, pk);
         }
@@ -223,8 +258,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         return t.x + t.y;
       };
       if (j == 0) m_ref = row_max();
-      mbar_wait(p_empty, (j & 1) ^ 1);                      // P V of the previous tile has consumed P (and updated O)
-      tc_fence_after();
+      if (!DEFER) {
+        mbar_wait(p_empty, (j & 1) ^ 1);                    // P V of the previous tile has consumed P (and updated O)
+        tc_fence_after();
+      }
       float tile_sum = exp_tile(m_ref * p.scale_log2);
       if (__any_sync(0xffffffffu, !(tile_sum <= 32768.0f))) {
         // rare, and taken by the whole warp (tcgen05.ld/st are warp-collective): bring O (TMEM) and l to the new reference
@@ -321,9 +358,19 @@ extern "C" int dwb_attention_fwd_tc(const void* q, int64_t ldq, const void* k, i
   if ((rc = make_tmap_bsc(&tk, k, ldk, B, Sk, H * TA_HD))) return rc;
   if ((rc = make_tmap_bsc(&tv, v, ldv, B, Sk, H * TA_HD))) return rc;
   if ((rc = make_tmap_bsc(&to, o, ldo, B, Sq, H * TA_HD))) return rc;
+  // DWB_ATTN_POLY = eighths of the exponentials emulated on the FMA pipe (0..4) + 10 * (deferred P wait): A/B switch for the
+  // microbenchmarks; the default is the measured best (profiles/r02_attention_variants.md)
+  static const int variant = [] { const char* e = getenv("DWB_ATTN_POLY"); return e ? atoi(e) : TA_DEFAULT_VARIANT; }();
+  const int np8 = variant % 10 < 0 ? 0 : (variant % 10 > 4 ? 4 : variant % 10);
+  const bool defer = variant >= 10;
+  typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcAttnParams);
+  static const kern_t table[2][5] = {
+      {attn_fwd_tc_kernel<0, false>, attn_fwd_tc_kernel<1, false>, attn_fwd_tc_kernel<2, false>, attn_fwd_tc_kernel<3, false>, attn_fwd_tc_kernel<4, false>},
+      {attn_fwd_tc_kernel<0, true>, attn_fwd_tc_kernel<1, true>, attn_fwd_tc_kernel<2, true>, attn_fwd_tc_kernel<3, true>, attn_fwd_tc_kernel<4, true>}};
   static bool attr = false;
   if (!attr) {
-    DWB_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 5; ++b) DWB_CUDA_OK(cudaFuncSetAttribute(table[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
     attr = true;
   }
   TcAttnParams p;
@@ -342,7 +389,7 @@ extern "C" int dwb_attention_fwd_tc(const void* q, int64_t ldq, const void* k, i
   //  two softmax warpgroups -- measured 0.63 ms with and without the ping-pong: one MMA-issuing thread serving two tiles in
   //  program order and a single softmax warp per SM sub-partition on the XU pipe at a time are both worse than two
   //  independent CTAs.  See profiles/README.md.)
-  attn_fwd_tc_kernel<<<grid, TA_THREADS, TA_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, to, p);
+  table[defer ? 1 : 0][np8]<<<grid, TA_THREADS, TA_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, to, p);
   DWB_LAUNCH_OK();
   return DWB_OK;
 }

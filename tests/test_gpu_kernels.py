@@ -377,7 +377,8 @@ def test_device_collator_matches_reference_collator_semantics():
     dec_ref, lab_ref = wo.collate_labels(rows, pad, sot, max_len=14)
     assert batch["decoder_input_ids"].is_cuda and torch.equal(batch["decoder_input_ids"].cpu(), dec_ref)
     assert torch.equal(batch["labels"].cpu(), lab_ref), (batch["labels"].cpu(), lab_ref)
-    assert (lab_ref[1, :4] == -100).all() and lab_ref[1, 4] == 12 and lab_ref[3, 2] == 2     # the fixture exercises the prompt mask
+    # the fixture exercises the prompt mask: row 1's labels are [3, 4, SOT, 11, 12, 13] -> masked up to and including SOT
+    assert (lab_ref[1, :3] == -100).all() and lab_ref[1, 3] == 11 and (lab_ref[3, :2] == -100).all() and lab_ref[3, 2] == 2
     want = fe.extract_device(torch.from_numpy(fe.pad_or_trim([f["input_values"] for f in feats_in])).cuda())
     assert batch["input_features"].shape == (4, 80, 3000) and torch.equal(batch["input_features"], want)
     ref0 = lo.log_mel(fe.pad_or_trim([feats_in[1]["input_values"]]), 80)

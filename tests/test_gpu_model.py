@@ -491,6 +491,7 @@ def test_integration_stub_loop_matches_the_reference_loop():
     ref_opt = torch.optim.AdamW(grouped(hf_s), lr=lr, betas=(0.9, 0.999), eps=1e-8)
     ref_sched = get_scheduler("linear", optimizer=ref_opt, num_warmup_steps=1, num_training_steps=4)
     batches = [_cuda(wo.synthetic_batch(sc, batch=3, n_tok=12, seed=s)) for s in (5, 6, 7, 8)]
+    init = {n: p.detach().clone() for n, p in hf_s.named_parameters() if p.requires_grad}
 
     def ref_micro(batch):
         hf_s.train()
@@ -530,10 +531,14 @@ def test_integration_stub_loop_matches_the_reference_loop():
             kd = DistillationStep(student, teacher, kl_weight=1.0, share_hidden_states=True)
     assert opt.step_count == 2 and abs(opt.param_groups[0]["lr"] - ref_opt.param_groups[0]["lr"]) < 1e-12
     hp = dict(hf_s.named_parameters())
-    worst = 0.0
-    for n, p in student.named_parameters():
-        if p.requires_grad:
-            worst = max(worst, _rel(p.detach(), hp[n].detach()))
-    # two AdamW steps of size ~lr on weights of size ~0.02: a sign flip of m/sqrt(v) on one near-zero gradient element moves that
-    # element by 2*lr; the bound is on the whole-tensor relative L2
-    assert worst < 2e-2, worst
+    # AdamW's first steps move every element by ~lr * sign(gradient): where |gradient| is below the bf16 noise of the CUDA
+    # path the sign is a coin toss for BOTH implementations, so single small tensors (biases) may differ by O(lr) per element.
+    # The checks are therefore on the whole parameter vector and on the direction of the total update.
+    ours = torch.cat([p.detach().reshape(-1) for n, p in student.named_parameters() if p.requires_grad]).double()
+    ref = torch.cat([hp[n].detach().reshape(-1) for n, p in student.named_parameters() if p.requires_grad]).double()
+    start = torch.cat([init[n].reshape(-1) for n, p in student.named_parameters() if p.requires_grad]).double()
+    assert float((ours - ref).norm() / ref.norm()) < 2e-2
+    du, dr = ours - start, ref - start
+    cos = float((du * dr).sum() / (du.norm() * dr.norm()))
+    assert cos > 0.9, cos
+    assert abs(float(du.norm() / dr.norm()) - 1.0) < 0.1
