@@ -27,7 +27,7 @@ constexpr int TA_BAR_BYTES = 112;
 constexpr int TA_SMEM = 115712;
 static_assert(TA_TILES_BYTES + TA_BAR_BYTES + 896 <= TA_SMEM, "smem budget");
 constexpr int TA_TMEM_COLS = 256;
-constexpr int TA_DEFAULT_VARIANT = 0;   // np8 + 10 * defer (see dwb_attention_fwd_tc)
+constexpr int TA_DEFAULT_VARIANT = 0;   // np8 + 10 * mode (see dwb_attention_fwd_tc)
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -63,9 +63,10 @@ struct TcAttnParams {
 
 // NP8: of every 8 score pairs, NP8 take the polynomial exp2 (spread evenly through the unrolled loop so that FMA-pipe chains
 // fill the issue slots between MUFU issues); 0 = all MUFU.
-// DEFER: the wait for "P V of the previous tile has consumed P" is taken after the first 64 exponentials of the tile are in
-// registers instead of before the first one, so that the previous tile's P V (and its completion signalling) runs under them.
-template <int NP8, bool DEFER>
+// MODE 1 (DEFER): the wait for "P V of the previous tile has consumed P" is taken after the first 64 exponentials of the tile
+// are in registers instead of before the first one, so that the previous tile's P V (and its completion signalling) runs under them.
+// MODE 2 (PIPE): software-pipelined softmax loop -- see the branch below.
+template <int NP8, int MODE>
 __global__ void __launch_bounds__(TA_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
@@ -190,7 +191,122 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const uint32_t t_p = tmem_p + ((uint32_t)(warp * 32) << 16);
     const int sw = row & 7;
     float m_ref = -INFINITY, l_run = 0.f;
+    constexpr bool DEFER = MODE == 1;
 
+    if constexpr (MODE == 2) {
+      // Software-pipelined variant.  The scores of tile j+1 are pulled from TMEM 32 columns at a time INTO THE REGISTERS THE
+      // exponentials of tile j have just released, so the TMEM read (64 B/clk per sub-partition: 256 cycles per tile) runs under
+      // the MUFU work instead of in front of it, and "scores are in registers" (-> Q K^T of tile j+2 may be issued) is signalled
+      // one tile earlier.  The row maximum of every tile is taken up front (FMNMX3 tree, ~45 instructions on the otherwise idle
+      // ALU pipe): exponentials are then bounded by 2^8 relative to the reference maximum, O is rescaled only when a row's
+      // maximum grows by more than 2^8 ("lazy rescale"), and no tile is ever exponentiated twice.
+      uint32_t v[128];
+      mbar_wait(s_full, 0);
+      tc_fence_after();
+      tmem_ld_32x32(t_s, v);
+      tmem_ld_32x32(t_s + 32, v + 32);
+      tmem_ld_32x32(t_s + 64, v + 64);
+      tmem_ld_32x32(t_s + 96, v + 96);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_empty);
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+      for (int j = 0; j < n_kv; ++j) {
+        const int kbase = j * TA_BK;
+        const bool tail = kbase + TA_BK > p.Sk;
+        const bool diag = p.causal && (kbase + TA_BK - 1 > q0);
+        if (tail || diag) {
+          const int lim = diag ? min(p.Sk, q0 + row + 1) : p.Sk;
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (kbase + i >= lim) v[i] = __float_as_uint(-INFINITY);
+        }
+        float mxp[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) mxp[c] = __uint_as_float(v[c]);
+#pragma unroll
+        for (int i = 8; i < 128; i += 8) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) mxp[c] = fmaxf(mxp[c], __uint_as_float(v[i + c]));
+        }
+        const float tmax = fmaxf(fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3])), fmaxf(fmaxf(mxp[4], mxp[5]), fmaxf(mxp[6], mxp[7])));
+        bool p_waited = false;
+        if (j == 0) {
+          m_ref = tmax;
+        } else if (__any_sync(0xffffffffu, (tmax - m_ref) * p.scale_log2 > 8.0f)) {
+          // rare, warp-uniform: bring O (TMEM) and l to the new reference maximum; rows that do not need it keep theirs (f = 1)
+          mbar_wait(p_empty, (j & 1) ^ 1);                  // P V of the previous tile has completed: O is stable
+          tc_fence_after();
+          p_waited = true;
+          const float mx = fmaxf(m_ref, tmax);
+          const float f = fast_exp2((m_ref - mx) * p.scale_log2);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(t_o + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st_32x32(t_o + c * 32, o);
+          }
+          tmem_st_wait();
+          l_run *= f;
+          m_ref = mx;
+        }
+        const float msc = m_ref * p.scale_log2;
+        const float2 nm2 = make_float2(-msc, -msc);
+        float2 ls[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        const bool more = j + 1 < n_kv;
+        auto exp_keys = [&](const int base, const int n, uint32_t* pk) {          // keys [base, base + n) -> n / 2 packed columns
+#pragma unroll
+          for (int i = 0; i < n; i += 2) {
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[base + i]), __uint_as_float(v[base + i + 1])), sc2, nm2);
+            float2 e;
+            if (((((base + i) >> 1) * NP8) & 7) < NP8) {
+              e = poly_exp2_pair(x);
+            } else {
+              e.x = fast_exp2(x.x);
+              e.y = fast_exp2(x.y);
+            }
+            ls[(i >> 1) & 3] = __fadd2_rn(ls[(i >> 1) & 3], e);
+            pk[i >> 1] = pack_bf16x2(e.x, e.y);
+          }
+        };
+        {
+          // first half of the tile: its 64 exponentials run while P V of the previous tile and Q K^T of the next one complete
+          uint32_t pk[32];
+          exp_keys(0, 64, pk);
+          if (!p_waited) {
+            mbar_wait(p_empty, (j & 1) ^ 1);                // P V of the previous tile has consumed P
+            tc_fence_after();
+          }
+          tmem_st_32x32(t_p, pk);
+          if (more) {
+            mbar_wait(s_full, (j + 1) & 1);                 // Q K^T of the next tile (issued when this tile's scores left TMEM)
+            tc_fence_after();
+            tmem_ld_32x32(t_s, v);                          // next tile's scores into the registers this half has released
+            tmem_ld_32x32(t_s + 32, v + 32);
+          }
+        }
+#pragma unroll
+        for (int c = 2; c < 4; ++c) {                       // 32 keys -> 16 packed columns per tcgen05.st
+          uint32_t pk[16];
+          exp_keys(c * 32, 32, pk);
+          tmem_st_32x16(t_p + c * 16, pk);
+          if (more) tmem_ld_32x32(t_s + c * 32, v + c * 32);
+        }
+        const float2 t = __fadd2_rn(__fadd2_rn(ls[0], ls[1]), __fadd2_rn(ls[2], ls[3]));
+        l_run += t.x + t.y;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_full);
+        if (more) {
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(s_empty);                             // tile j+1's scores are in registers: Q K^T of tile j+2 may start
+        }
+      }
+    } else
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
@@ -358,18 +474,19 @@ extern "C" int dwb_attention_fwd_tc(const void* q, int64_t ldq, const void* k, i
   if ((rc = make_tmap_bsc(&tk, k, ldk, B, Sk, H * TA_HD))) return rc;
   if ((rc = make_tmap_bsc(&tv, v, ldv, B, Sk, H * TA_HD))) return rc;
   if ((rc = make_tmap_bsc(&to, o, ldo, B, Sq, H * TA_HD))) return rc;
-  // DWB_ATTN_POLY = eighths of the exponentials emulated on the FMA pipe (0..4) + 10 * (deferred P wait): A/B switch for the
-  // microbenchmarks; the default is the measured best (profiles/r02_attention_variants.md)
+  // DWB_ATTN_POLY = eighths of the exponentials emulated on the FMA pipe (0..4) + 10 * mode (0 original loop, 1 deferred P wait,
+  // 2 software-pipelined loop): A/B switch for the microbenchmarks; the default is the measured best (profiles/)
   static const int variant = [] { const char* e = getenv("DWB_ATTN_POLY"); return e ? atoi(e) : TA_DEFAULT_VARIANT; }();
-  const int np8 = variant % 10 < 0 ? 0 : (variant % 10 > 4 ? 4 : variant % 10);
-  const bool defer = variant >= 10;
+  const int np8 = variant % 10 > 4 ? 4 : variant % 10;
+  const int mode = variant / 10 > 2 ? 2 : variant / 10;
   typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcAttnParams);
-  static const kern_t table[2][5] = {
-      {attn_fwd_tc_kernel<0, false>, attn_fwd_tc_kernel<1, false>, attn_fwd_tc_kernel<2, false>, attn_fwd_tc_kernel<3, false>, attn_fwd_tc_kernel<4, false>},
-      {attn_fwd_tc_kernel<0, true>, attn_fwd_tc_kernel<1, true>, attn_fwd_tc_kernel<2, true>, attn_fwd_tc_kernel<3, true>, attn_fwd_tc_kernel<4, true>}};
+  static const kern_t table[3][5] = {
+      {attn_fwd_tc_kernel<0, 0>, attn_fwd_tc_kernel<1, 0>, attn_fwd_tc_kernel<2, 0>, attn_fwd_tc_kernel<3, 0>, attn_fwd_tc_kernel<4, 0>},
+      {attn_fwd_tc_kernel<0, 1>, attn_fwd_tc_kernel<1, 1>, attn_fwd_tc_kernel<2, 1>, attn_fwd_tc_kernel<3, 1>, attn_fwd_tc_kernel<4, 1>},
+      {attn_fwd_tc_kernel<0, 2>, attn_fwd_tc_kernel<1, 2>, attn_fwd_tc_kernel<2, 2>, attn_fwd_tc_kernel<3, 2>, attn_fwd_tc_kernel<4, 2>}};
   static bool attr = false;
   if (!attr) {
-    for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < 3; ++a)
       for (int b = 0; b < 5; ++b) DWB_CUDA_OK(cudaFuncSetAttribute(table[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
     attr = true;
   }
@@ -389,7 +506,7 @@ extern "C" int dwb_attention_fwd_tc(const void* q, int64_t ldq, const void* k, i
   //  two softmax warpgroups -- measured 0.63 ms with and without the ping-pong: one MMA-issuing thread serving two tiles in
   //  program order and a single softmax warp per SM sub-partition on the XU pipe at a time are both worse than two
   //  independent CTAs.  See profiles/README.md.)
-  table[defer ? 1 : 0][np8]<<<grid, TA_THREADS, TA_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, to, p);
+  table[mode][np8]<<<grid, TA_THREADS, TA_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, to, p);
   DWB_LAUNCH_OK();
   return DWB_OK;
 }
