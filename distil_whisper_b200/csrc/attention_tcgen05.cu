@@ -27,7 +27,7 @@ constexpr int TA_BAR_BYTES = 112;
 constexpr int TA_SMEM = 115712;
 static_assert(TA_TILES_BYTES + TA_BAR_BYTES + 896 <= TA_SMEM, "smem budget");
 constexpr int TA_TMEM_COLS = 256;
-constexpr int TA_DEFAULT_VARIANT = 0;   // np8 + 10 * mode (see dwb_attention_fwd_tc)
+constexpr int TA_DEFAULT_VARIANT = 1;   // np8 + 10 * mode (see dwb_attention_fwd_tc)
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
