@@ -523,10 +523,13 @@ def test_integration_stub_loop_matches_the_reference_loop():
                 student2 = DistilWhisperB200ForConditionalGeneration.from_pretrained(d).cuda()
             for p in student2.model.encoder.parameters():
                 p.requires_grad = False
+            # the order accelerate's load_state uses: objects are built first, then optimizer state (which carries the
+            # current lr of every group), then scheduler state
             opt2 = FusedAdamW(grouped(student2), lr=lr, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=clip)
-            opt2.load_state_dict(osd)
             sched2 = get_scheduler("linear", optimizer=opt2, num_warmup_steps=1, num_training_steps=4)
+            opt2.load_state_dict(osd)
             sched2.load_state_dict(sched.state_dict())
+            assert opt2.param_groups[0]["lr"] == opt.param_groups[0]["lr"] > 0
             student, opt, sched = student2, opt2, sched2
             kd = DistillationStep(student, teacher, kl_weight=1.0, share_hidden_states=True)
     assert opt.step_count == 2 and abs(opt.param_groups[0]["lr"] - ref_opt.param_groups[0]["lr"]) < 1e-12
@@ -539,6 +542,8 @@ def test_integration_stub_loop_matches_the_reference_loop():
     start = torch.cat([init[n].reshape(-1) for n, p in student.named_parameters() if p.requires_grad]).double()
     assert float((ours - ref).norm() / ref.norm()) < 2e-2
     du, dr = ours - start, ref - start
-    cos = float((du * dr).sum() / (du.norm() * dr.norm()))
-    assert cos > 0.9, cos
-    assert abs(float(du.norm() / dr.norm()) - 1.0) < 0.1
+    n_du, n_dr = float(du.norm()), float(dr.norm())
+    assert n_du > 0 and n_dr > 0, (n_du, n_dr, float(ours.norm()), float(ref.norm()), float(start.norm()))
+    cos = float((du * dr).sum()) / (n_du * n_dr)
+    assert cos > 0.9, (cos, n_du, n_dr)
+    assert abs(n_du / n_dr - 1.0) < 0.1, (n_du, n_dr)
