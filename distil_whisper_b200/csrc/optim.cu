@@ -60,11 +60,24 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
 
 using namespace dwb;
 
+// Upper bound on the grid of the optimiser-tail kernels (0 = fill the machine).  When the tail runs on a side stream underneath
+// the next step's encoder forward (kd.PipelinedTrainer), a machine-filling grid of short CTAs takes register file and thread
+// slots away from the persistent one-CTA-per-SM GEMM kernels at every one of their launches and stretches them; a few dozen
+// long-running CTAs (256 threads, ~32 registers: co-resident with a GEMM CTA) stream the same bytes under the 75 ms of encoder
+// work without ever holding an SM back.
+static int g_tail_grid = 0;
+extern "C" int dwb_set_tail_grid(int ctas) {
+  DWB_CHECK_ARG(ctas >= 0, "dwb_set_tail_grid: negative grid");
+  g_tail_grid = ctas;
+  return DWB_OK;
+}
+
 extern "C" int dwb_grad_sumsq(const float* g, int64_t n, float* out_accum, void* stream) {
   DWB_CHECK_ARG(g && out_accum && n > 0, "dwb_grad_sumsq: bad args");
   DWB_CHECK_ARG((reinterpret_cast<uintptr_t>(g) & 15) == 0, "dwb_grad_sumsq: buffer must be 16 B aligned");
   int64_t blocks = ceil_div64(n / 4 + 1, 256);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  if (g_tail_grid > 0 && blocks > g_tail_grid) blocks = g_tail_grid;
   sumsq_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, n, out_accum);
   DWB_LAUNCH_OK();
   return DWB_OK;
@@ -82,6 +95,7 @@ extern "C" int dwb_adamw_step(float* p, float* g, float* m, float* v, void* p_bf
   a.grad_scale = grad_scale;
   int64_t blocks = ceil_div64(n, 256);
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  if (g_tail_grid > 0 && blocks > g_tail_grid) blocks = g_tail_grid;
   adamw_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)p_bf16, n, grad_sumsq, a, zero_grad);
   DWB_LAUNCH_OK();
   return DWB_OK;

@@ -206,8 +206,13 @@ class PipelinedTrainer:
     """
 
     def __init__(self, step: DistillationStep, optimizer, example_batch: dict, temperature: float = 2.0,
-                 gradient_accumulation_steps: int = 1, group=None, warmup: int = 2):
+                 gradient_accumulation_steps: int = 1, group=None, warmup: int = 2, tail_grid: int | None = None):
         self.kd, self.opt, self.group = step, optimizer, group
+        # grid cap of the overlapped clip + AdamW kernels (see dwb_set_tail_grid); DWB_TAIL_GRID overrides for A/B runs
+        import os
+        from . import _abi
+        self.tail_grid = int(os.environ.get("DWB_TAIL_GRID", 48 if tail_grid is None else tail_grid))
+        self._abi = _abi
         self.accum = int(gradient_accumulation_steps)
         if self.accum < 1:
             raise ValueError("gradient_accumulation_steps must be >= 1")
@@ -254,7 +259,11 @@ class PipelinedTrainer:
                 with engine.nvtx_range("dwb.grad_all_reduce"):
                     self.opt.all_reduce_gradients(self.group)
                 with engine.nvtx_range("dwb.clip_adamw"):
-                    self.opt.step()
+                    self._abi.call("dwb_set_tail_grid", self.tail_grid)      # host-side launch parameter of the next two kernels only
+                    try:
+                        self.opt.step()
+                    finally:
+                        self._abi.call("dwb_set_tail_grid", 0)
                 self.tail_done.record(self.side)
             self._tail_pending = True
         return self.loss

@@ -143,6 +143,9 @@ int dwb_kd_loss(const float* student_logits, const float* teacher_logits, int64_
 
 /* ---- optimiser tail: ref:training/run_distillation.py:1610-1614 (clip_grad_norm_, AdamW.step, zero_grad) -------*/
 int dwb_grad_sumsq(const float* g, int64_t n, float* out_accum, void* stream);
+/* Cap the grid of the two optimiser-tail kernels (0 = default: fill the machine).  Used when the tail is overlapped with the
+ * next step's encoder forward on a side stream, so that it never takes an SM away from the persistent GEMM kernels. */
+int dwb_set_tail_grid(int ctas);
 int dwb_adamw_step(float* p, float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
                    float weight_decay, int step, const float* grad_sumsq, float max_grad_norm, float grad_scale, int zero_grad,
                    void* stream);
