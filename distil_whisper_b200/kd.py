@@ -208,10 +208,13 @@ class PipelinedTrainer:
     def __init__(self, step: DistillationStep, optimizer, example_batch: dict, temperature: float = 2.0,
                  gradient_accumulation_steps: int = 1, group=None, warmup: int = 2, tail_grid: int | None = None):
         self.kd, self.opt, self.group = step, optimizer, group
-        # grid cap of the overlapped clip + AdamW kernels (see dwb_set_tail_grid); DWB_TAIL_GRID overrides for A/B runs
+        # optional grid cap of the overlapped clip + AdamW kernels (dwb_set_tail_grid; 0 = none).  Measured at N = 1
+        # (profiles/r02_tail_overlap.md): serial tail, overlapped tail and capped grids are within noise of each other (the
+        # kernels themselves take 0.85 ms); the side stream pays off through the NCCL all-reduce at N > 1.
         import os
         from . import _abi
-        self.tail_grid = int(os.environ.get("DWB_TAIL_GRID", 48 if tail_grid is None else tail_grid))
+        self.tail_grid = int(os.environ.get("DWB_TAIL_GRID", 0 if tail_grid is None else tail_grid))
+        self.overlap = os.environ.get("DWB_TAIL_OVERLAP", "1") != "0"      # 0: tail on the main stream (A/B)
         self._abi = _abi
         self.accum = int(gradient_accumulation_steps)
         if self.accum < 1:
@@ -252,7 +255,10 @@ class PipelinedTrainer:
         self.g_dec.replay()
         self._micro += 1
         run_tail = (self._micro % self.accum == 0) if tail is None else tail
-        if run_tail:
+        if run_tail and not self.overlap:
+            self.opt.all_reduce_gradients(self.group)
+            self.opt.step()
+        elif run_tail:
             self.bwd_done.record(main)
             with torch.cuda.stream(self.side):
                 self.side.wait_event(self.bwd_done)
