@@ -58,9 +58,13 @@ SIGNATURES = {
     "dwb_logmel_plan_create": (_i, [_p, _i, _i, C.POINTER(_p)]),
     "dwb_logmel_plan_destroy": (_i, [_p]),
     "dwb_logmel": (_i, [_p, _p, _i, _i, _p, _p]),
+    "dwb_logmel_tc_plan_create": (_i, [_p, _i, _i, C.POINTER(_p)]),
+    "dwb_logmel_tc_plan_destroy": (_i, [_p]),
+    "dwb_logmel_tc_workspace_bytes": (_l, [_i, _i]),
+    "dwb_logmel_tc": (_i, [_p, _p, _i, _i, _p, _p, _p]),
 }
 
-_NO_STATUS = {"dwb_last_error", "dwb_abi_version", "dwb_kd_loss_workspace_bytes", "dwb_launch_count"}
+_NO_STATUS = {"dwb_last_error", "dwb_abi_version", "dwb_kd_loss_workspace_bytes", "dwb_launch_count", "dwb_logmel_tc_workspace_bytes"}
 
 
 class DwbError(RuntimeError):

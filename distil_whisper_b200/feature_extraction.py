@@ -63,6 +63,8 @@ class WhisperFeatureExtractorB200:
         self.nb_max_frames = self.n_samples // hop_length
         self.mel_filters = slaney_mel_filter_bank(1 + n_fft // 2, feature_size, 0.0, 8000.0, sampling_rate)
         self._plan = None
+        self._plan_tc = None
+        self._ws = None
 
     # -- (de)serialisation: ref:training/run_distillation.py:1071, :1641, :1754, :1783 call feature_extractor.save_pretrained ----
     def to_dict(self):
@@ -103,18 +105,39 @@ class WhisperFeatureExtractorB200:
         try:
             if getattr(self, "_plan", None) is not None:
                 _abi.call("dwb_logmel_plan_destroy", self._plan)
+            if getattr(self, "_plan_tc", None) is not None:
+                _abi.call("dwb_logmel_tc_plan_destroy", self._plan_tc)
         except Exception:  # noqa: BLE001  (interpreter shutdown)
             pass
 
-    def extract_device(self, wav: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
-        """wav: CUDA fp32 [B, n_samples] (already padded / truncated).  Returns CUDA fp32 [B, n_mels, n_samples/160]."""
+    def _get_plan_tc(self):
+        if self._plan_tc is None:
+            filt = np.ascontiguousarray(self.mel_filters.astype(np.float32))
+            plan = C.c_void_p()
+            _abi.call("dwb_logmel_tc_plan_create", filt.ctypes.data_as(C.c_void_p), filt.shape[0], filt.shape[1], C.byref(plan))
+            self._plan_tc = plan
+        return self._plan_tc
+
+    def extract_device(self, wav: torch.Tensor, out: torch.Tensor | None = None, impl: str = "tc") -> torch.Tensor:
+        """wav: CUDA fp32 [B, n_samples] (already padded / truncated).  Returns CUDA fp32 [B, n_mels, n_samples/160].
+        impl "tc": the DFT as a tcgen05 GEMM (dwb_logmel_tc, the product path); "fft": the shared-memory FFT kernel
+        (dwb_logmel), kept as an on-device cross-check."""
         if not (wav.is_cuda and wav.dtype == torch.float32 and wav.dim() == 2 and wav.is_contiguous()):
             raise ValueError("extract_device expects a contiguous CUDA float32 [B, n_samples] tensor")
         B, n = wav.shape
         if out is None:
             out = torch.empty((B, self.feature_size, n // self.hop_length), dtype=torch.float32, device=wav.device)
-        _abi.call("dwb_logmel", self._get_plan(), C.c_void_p(wav.data_ptr()), B, n, C.c_void_p(out.data_ptr()),
-                  C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if impl == "fft":
+            _abi.call("dwb_logmel", self._get_plan(), C.c_void_p(wav.data_ptr()), B, n, C.c_void_p(out.data_ptr()), stream)
+            return out
+        if impl != "tc":
+            raise ValueError(f"unknown log-mel implementation {impl!r}")
+        need = int(_abi.call("dwb_logmel_tc_workspace_bytes", B, n))
+        if self._ws is None or self._ws.numel() < need or self._ws.device != wav.device:
+            self._ws = torch.empty((need,), dtype=torch.uint8, device=wav.device)
+        _abi.call("dwb_logmel_tc", self._get_plan_tc(), C.c_void_p(wav.data_ptr()), B, n, C.c_void_p(out.data_ptr()),
+                  C.c_void_p(self._ws.data_ptr()), stream)
         return out
 
     # -- HF-compatible surface -------------------------------------------------------------------------------

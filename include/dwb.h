@@ -157,6 +157,15 @@ int dwb_logmel_plan_create(const float* mel_filters_host, int n_freq, int n_mels
 int dwb_logmel_plan_destroy(void* plan);
 int dwb_logmel(void* plan, const float* wav, int B, int n_samples, float* out, void* stream);
 
+/* Same contract on the tensor cores: the windowed 400-point DFT of every frame as a tcgen05 GEMM (fp16 hi/lo split of both
+ * operands, three MMAs per k-step, fp32 accumulation in TMEM), the overlapping frames delivered by TMA through a tensor map with a
+ * 160-sample frame stride, mel / log10 / per-utterance maximum in the epilogue.  workspace: dwb_logmel_tc_workspace_bytes(B,
+ * n_samples) bytes, 256 B aligned, caller-owned (fp16 copies of one chunk of padded waveforms + per-utterance maxima). */
+int dwb_logmel_tc_plan_create(const float* mel_filters_host, int n_freq, int n_mels, void** plan_out);
+int dwb_logmel_tc_plan_destroy(void* plan);
+int64_t dwb_logmel_tc_workspace_bytes(int B, int n_samples);
+int dwb_logmel_tc(void* plan, const float* wav, int B, int n_samples, float* out, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
