@@ -12,7 +12,12 @@
  *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream and re-entrant.
  *   - "bf16" buffers are __nv_bfloat16; matrices are row-major with an explicit row pitch `ld*` in ELEMENTS.
  *   - TMA-backed operands (GEMM A/B/C) need a 16-byte aligned base and a row pitch that is a multiple of 16 bytes.
- *   - no hidden global state except immutable tables created by *_plan_create.
+ *   - no hidden global state except immutable tables created by *_plan_create (the tensor-core log-mel plan also owns two
+ *     internal streams + events for its chunk pipeline: one dwb_logmel_tc call at a time per plan), the launch counter and the
+ *     optimiser-tail grid cap.
+ *   - host-side contract of the Python layer built on this ABI (distil_whisper_b200/): parameter gradients are written by these kernels
+ *     straight into caller-owned flat fp32 buffers (TMA reduce-add / atomics), never through autograd hooks -- a data-parallel user
+ *     all-reduces that buffer once per optimiser step (optim.FusedAdamW.all_reduce_gradients) instead of wrapping the model in DDP.
  */
 #ifndef DWB_H_
 #define DWB_H_
