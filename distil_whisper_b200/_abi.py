@@ -45,6 +45,7 @@ SIGNATURES = {
     "dwb_embed_decode": (_i, [_p, _i, _p, _p, _p, _i, _p, _i, _i, _i, _p]),
     "dwb_attention_decode": (_i, [_p, _l, _p, _p, _l, _p, _p, _l, _i, _p, _l, _i, _i, _i, _i, _p, _f, _p]),
     "dwb_greedy_pick": (_i, [_p, _l, _i, _p, _p, _i, _p, _i, _i, _p, _l, _l, _p, _i, _p]),
+    "dwb_greedy_pick_timestamps": (_i, [_p, _l, _i, _p, _p, _i, _p, _i, _i, _p, _l, _l, _p, _i, _i, _i, _p]),
     "dwb_decode_advance": (_i, [_p, _p, _i, _p, _p]),
     "dwb_collate_labels": (_i, [_p, _p, _i, _i, _l, _p, _p, _p]),
     "dwb_colsum_bf16": (_i, [_p, _l, _p, _i, _i, _i, _p]),

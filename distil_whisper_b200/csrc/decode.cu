@@ -189,6 +189,101 @@ __global__ void __launch_bounds__(GP_THREADS) greedy_pick_kernel(const float* __
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Greedy pick under Whisper's timestamp rules (HF:generation/logits_process.py WhisperTimeStampLogitsProcessor, applied after the two
+// suppress processors like HF:models/whisper/generation_whisper.py:1774-1800 orders them), for `return_timestamps=True` -- the
+// reference's recommended pseudo-labelling mode (ref:training/README.md:130,148).  With g = the tokens generated so far (after the
+// initial tokens), ts = ids >= ts_begin (= <|notimestamps|> + 1):
+//   <|notimestamps|> is never emitted; after a timestamp that closes a pair (or opens the transcript) no timestamp may follow, after a
+//   text token followed by one timestamp no text below EOS may follow; timestamps never decrease (and <|0.00|> is not repeated);
+//   the first generated token is a timestamp no later than max_initial_timestamp_index; and whenever the probability mass of all
+//   timestamps exceeds the most probable text token, a timestamp is forced.  All masks are index ranges, so one scan of the row that
+//   tracks (best text token, best timestamp, max text logit, log-sum-exp of the timestamp logits) decides the pick.
+struct TimestampRules {
+  int ts_begin, no_ts, eos, max_initial;     // max_initial < 0: no limit
+};
+__global__ void __launch_bounds__(GP_THREADS) greedy_pick_ts_kernel(const float* __restrict__ logits, int64_t ld, int vocab,
+                                                                    const float* __restrict__ bias_all, const float* __restrict__ bias_begin,
+                                                                    int begin_pos, int64_t* __restrict__ seq, int seq_ld, int prompt_len,
+                                                                    int* __restrict__ finished, int64_t eos, int64_t pad,
+                                                                    const int* __restrict__ pos_dev, TimestampRules r) {
+  __shared__ float s_f[4][GP_THREADS / 32];
+  __shared__ int s_i[3][GP_THREADS / 32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nxt = *pos_dev + 1;
+  if (nxt < prompt_len || nxt >= seq_ld) return;
+  if (finished[b]) {
+    if (tid == 0) seq[(int64_t)b * seq_ld + nxt] = pad;
+    return;
+  }
+  const int64_t* srow = seq + (int64_t)b * seq_ld;
+  // ---- state of the generated part g = srow[begin_pos .. nxt)
+  const int n_gen = nxt - begin_pos;
+  const bool last_ts = n_gen >= 1 && srow[nxt - 1] >= r.ts_begin;
+  const bool penult_ts = n_gen < 2 || srow[nxt - 2] >= r.ts_begin;
+  int last_idx = -1;                                        // index of the last timestamp token in g
+  for (int i = begin_pos + tid; i < nxt; i += GP_THREADS)
+    if (srow[i] >= r.ts_begin) last_idx = i;                // per-thread indices increase
+  last_idx = __reduce_max_sync(0xffffffffu, last_idx);
+  if (lane == 0) s_i[0][warp] = last_idx;
+  __syncthreads();
+  last_idx = s_i[0][0];
+  for (int w = 1; w < GP_THREADS / 32; ++w) last_idx = max(last_idx, s_i[0][w]);
+  __syncthreads();
+  int ts_floor = r.ts_begin;                                // timestamps below this are forbidden
+  if (last_idx >= 0) ts_floor = (int)srow[last_idx] + ((last_ts && !penult_ts) ? 0 : 1);
+  const bool at_begin = nxt == begin_pos;
+  const int text_hi = at_begin ? 0 : r.ts_begin;            // text tokens [text_lo, text_hi) are allowed
+  const int text_lo = (last_ts && !penult_ts) ? r.eos : 0;
+  const bool ts_allowed = !(last_ts && penult_ts);
+  const int ts_hi = (at_begin && r.max_initial >= 0) ? min(vocab, r.ts_begin + r.max_initial + 1) : vocab;
+  // ---- one scan
+  const float* row = logits + (int64_t)b * ld;
+  const bool use_begin_bias = bias_begin != nullptr && at_begin;
+  float bt = -INFINITY, bs = -INFINITY, m_ts = -INFINITY, z_ts = 0.f;
+  int bt_i = 0x7fffffff, bs_i = 0x7fffffff;
+  for (int c = tid; c < vocab; c += GP_THREADS) {
+    float v = row[c];
+    if (bias_all) v += bias_all[c];
+    if (use_begin_bias) v += bias_begin[c];
+    if (c < r.ts_begin) {
+      if (c == r.no_ts || c < text_lo || c >= text_hi) continue;
+      if (v > bt) { bt = v; bt_i = c; }
+    } else {
+      if (!ts_allowed || c < ts_floor || c >= ts_hi) continue;
+      if (v > bs) { bs = v; bs_i = c; }
+      if (v > m_ts) { z_ts = z_ts * __expf(m_ts - v) + 1.f; m_ts = v; } else if (v > -INFINITY) { z_ts += __expf(v - m_ts); }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bt, o); const int oi = __shfl_xor_sync(0xffffffffu, bt_i, o);
+    if (ov > bt || (ov == bt && oi < bt_i)) { bt = ov; bt_i = oi; }
+    const float pv = __shfl_xor_sync(0xffffffffu, bs, o); const int pi = __shfl_xor_sync(0xffffffffu, bs_i, o);
+    if (pv > bs || (pv == bs && pi < bs_i)) { bs = pv; bs_i = pi; }
+    const float om = __shfl_xor_sync(0xffffffffu, m_ts, o), oz = __shfl_xor_sync(0xffffffffu, z_ts, o);
+    const float mm = fmaxf(m_ts, om);
+    if (mm > -INFINITY) { z_ts = z_ts * __expf(m_ts - mm) + oz * __expf(om - mm); m_ts = mm; }
+  }
+  if (lane == 0) { s_f[0][warp] = bt; s_i[1][warp] = bt_i; s_f[1][warp] = bs; s_i[2][warp] = bs_i; s_f[2][warp] = m_ts; s_f[3][warp] = z_ts; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < GP_THREADS / 32; ++w) {
+      if (s_f[0][w] > bt || (s_f[0][w] == bt && s_i[1][w] < bt_i)) { bt = s_f[0][w]; bt_i = s_i[1][w]; }
+      if (s_f[1][w] > bs || (s_f[1][w] == bs && s_i[2][w] < bs_i)) { bs = s_f[1][w]; bs_i = s_i[2][w]; }
+      const float mm = fmaxf(m_ts, s_f[2][w]);
+      if (mm > -INFINITY) { z_ts = z_ts * __expf(m_ts - mm) + s_f[3][w] * __expf(s_f[2][w] - mm); m_ts = mm; }
+    }
+    const float lse_ts = z_ts > 0.f ? m_ts + __logf(z_ts) : -INFINITY;
+    int pick;
+    if (lse_ts > bt) pick = bs_i;                           // the timestamps together outweigh every text token
+    else pick = (bs > bt) ? bs_i : bt_i;                    // plain arg-max (text indices are lower: ties go to text)
+    if (pick == 0x7fffffff) pick = (int)eos;                // everything masked (cannot happen with a sane config)
+    seq[(int64_t)b * seq_ld + nxt] = pick;
+    if ((int64_t)pick == eos) finished[b] = 1;
+  }
+}
+
 // pos += 1; done_at = first position count at which every row had finished (0 while some row is still decoding)
 __global__ void decode_advance_kernel(int* __restrict__ pos_dev, const int* __restrict__ finished, int B, int* __restrict__ done_at) {
   int all = 1;
@@ -246,6 +341,21 @@ extern "C" int dwb_greedy_pick(const float* logits, int64_t ld, int vocab, const
                 "dwb_greedy_pick: bad args");
   greedy_pick_kernel<<<B, GP_THREADS, 0, (cudaStream_t)stream>>>(logits, ld, vocab, bias_all, bias_begin, begin_pos, seq, seq_ld, prompt_len,
                                                                  finished, eos, pad, pos_dev);
+  DWB_LAUNCH_OK();
+  return DWB_OK;
+}
+
+extern "C" int dwb_greedy_pick_timestamps(const float* logits, int64_t ld, int vocab, const float* bias_all, const float* bias_begin,
+                                         int begin_pos, int64_t* seq, int seq_ld, int prompt_len, int* finished, int64_t eos, int64_t pad,
+                                         const int* pos_dev, int B, int timestamp_begin, int max_initial_timestamp_index, void* stream) {
+  DWB_CHECK_ARG(logits && seq && finished && pos_dev && B > 0 && vocab > 0 && ld >= vocab && prompt_len >= 1 && seq_ld >= prompt_len,
+                "dwb_greedy_pick_timestamps: bad args");
+  DWB_CHECK_ARG(timestamp_begin > 1 && timestamp_begin <= vocab && eos >= 0 && eos < timestamp_begin,
+                "dwb_greedy_pick_timestamps: timestamp_begin %d / eos %lld inconsistent with vocab %d", timestamp_begin, (long long)eos, vocab);
+  TimestampRules r;
+  r.ts_begin = timestamp_begin; r.no_ts = timestamp_begin - 1; r.eos = (int)eos; r.max_initial = max_initial_timestamp_index;
+  greedy_pick_ts_kernel<<<B, GP_THREADS, 0, (cudaStream_t)stream>>>(logits, ld, vocab, bias_all, bias_begin, begin_pos, seq, seq_ld, prompt_len,
+                                                                    finished, eos, pad, pos_dev, r);
   DWB_LAUNCH_OK();
   return DWB_OK;
 }

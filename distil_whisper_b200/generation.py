@@ -15,8 +15,11 @@ contract -- what the reference's `tokenizer.batch_decode(..., skip_special_token
 additionally strips the initial tokens / EOS and re-enters its long-form seek loop when a row hits max_length without EOS;
 after `skip_special_tokens` the strings are the same whenever EOS is reached.)
 
-Not implemented -> NotImplementedError (never a silently different decode): beam search, sampling, timestamp rules
-(`return_timestamps=True`), prompt_ids, custom logits processors, long-form (> 30 s) inputs.
+  * `return_timestamps=True` (the reference's recommended pseudo-labelling mode, ref:training/README.md:130,148): no
+    <|notimestamps|> in the initial tokens and WhisperTimeStampLogitsProcessor's rules (HF:generation/logits_process.py) inside the
+    token pick (dwb_greedy_pick_timestamps), `max_initial_timestamp_index` from the generation config.
+Not implemented -> NotImplementedError (never a silently different decode): beam search, sampling, prompt_ids, custom logits
+processors, long-form (> 30 s) inputs.
 
 Schedule: the encoder and the per-layer cross-attention K/V projections of its 1500 positions run once; then ONE CUDA graph
 of the single-token step (embedding at position pos, per layer LN -> QKV GEMM -> cache append + attention over pos+1 keys ->
@@ -120,6 +123,8 @@ def initial_tokens(model, gen, language, task, return_timestamps, detect):
         nots = _cfg_get(gen, "no_timestamps_token_id", None)
         if not return_timestamps and nots is not None and row[-1] != nots:
             row.append(nots)
+        elif return_timestamps and nots is not None and row[-1] == nots:
+            row.pop()                    # <|notimestamps|> from forced_decoder_ids is dropped when timestamps are requested
         rows[r] = [t for t in row if t is not None]
     return rows
 
@@ -152,7 +157,7 @@ class DecodeSession:
         self.logits = None
 
     # ---- one decoder step on the tokens at column pos (device scalar) --------------------------------------------
-    def _step(self, prompt_len, begin_pos, eos, pad):
+    def _step(self, prompt_len, begin_pos, eos, pad, ts_begin=None, max_initial=None):
         st, dec = self.st, self.st.m
         B, d, H, S, c = self.B, self.d, self.H, self.S, self.st.cache
         E, P = dec.embed_tokens.weight, dec.embed_positions.weight
@@ -182,11 +187,15 @@ class DecodeSession:
         g, b_ = engine._ln(st, "ln_f", dec.layer_norm)
         _, hf, _, _ = ops.add_layernorm(x, y, g, b_, rows=B, d=d, write_x=False)
         logits = engine.lm_head(st, hf)
-        ops.greedy_pick(logits, self.V, self.bias_all, self.bias_begin, begin_pos, self.seq, prompt_len, self.finished, eos, pad, self.pos)
+        if ts_begin is None:
+            ops.greedy_pick(logits, self.V, self.bias_all, self.bias_begin, begin_pos, self.seq, prompt_len, self.finished, eos, pad, self.pos)
+        else:       # return_timestamps=True: WhisperTimeStampLogitsProcessor's rules inside the pick
+            ops.greedy_pick_timestamps(logits, self.V, self.bias_all, self.bias_begin, begin_pos, self.seq, prompt_len, self.finished, eos, pad,
+                                       self.pos, ts_begin, max_initial)
         ops.decode_advance(self.pos, self.finished, self.done_at)
         return logits
 
-    def prepare(self, enc, prompt, suppress, begin_suppress, eos, pad):
+    def prepare(self, enc, prompt, suppress, begin_suppress, eos, pad, ts_begin=None, max_initial=None):
         """Load the encoder states, project the cross-attention K/V once per layer, reset the token matrix to the prompt."""
         st, dec = self.st, self.st.m
         d = self.d
@@ -201,7 +210,7 @@ class DecodeSession:
             self.bias_all[torch.as_tensor(sorted(set(suppress)), device=self.bias_all.device)] = float("-inf")
         if begin_suppress:
             self.bias_begin[torch.as_tensor(sorted(set(begin_suppress)), device=self.bias_all.device)] = float("-inf")
-        params = (prompt.shape[1], prompt.shape[1], int(eos), int(pad))
+        params = (prompt.shape[1], prompt.shape[1], int(eos), int(pad), ts_begin, max_initial)
         # one eager step: re-casts the bf16 shadows of weights the optimiser has changed since the last call (in place, so the
         # captured graph below keeps reading the right buffers), sets kernel attributes and warms the allocator
         self.params = params
@@ -258,8 +267,16 @@ def generate(model, input_features=None, decoder_input_ids=None, encoder_outputs
         num_beams = _cfg_get(gen, "num_beams", 1) or 1
     if return_timestamps is None:
         return_timestamps = bool(_cfg_get(gen, "return_timestamps", False))
-    if num_beams != 1 or do_sample or return_timestamps:
-        raise NotImplementedError("only greedy decoding (num_beams=1, do_sample=False, return_timestamps=False) is implemented")
+    if num_beams != 1 or do_sample:
+        raise NotImplementedError("only greedy decoding (num_beams=1, do_sample=False) is implemented")
+    ts_begin = max_initial = None
+    if return_timestamps:
+        nots = _cfg_get(gen, "no_timestamps_token_id", None)
+        if nots is None:
+            raise ValueError("You are trying to return timestamps, but the generation config is not properly set: it has no "
+                             "`no_timestamps_token_id`.")
+        ts_begin = int(nots) + 1
+        max_initial = _cfg_get(gen, "max_initial_timestamp_index", None)
     unsupported = [k for k in ("logits_processor", "prompt_ids", "forced_decoder_ids", "stopping_criteria", "assistant_model",
                                "prefix_allowed_tokens_fn", "temperature", "attention_mask") if kwargs.get(k) is not None]
     if unsupported:
@@ -324,7 +341,7 @@ def generate(model, input_features=None, decoder_input_ids=None, encoder_outputs
         if begin_suppress_tokens is None:
             begin_suppress_tokens = _cfg_get(gen, "begin_suppress_tokens", None)
         ses = _session(model, B, limit, S)
-        ses.prepare(enc, prompt, suppress_tokens, begin_suppress_tokens, eos, pad)
+        ses.prepare(enc, prompt, suppress_tokens, begin_suppress_tokens, eos, pad, ts_begin, max_initial)
         return ses.run(limit)
     finally:
         model.train(was_training)

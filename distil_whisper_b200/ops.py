@@ -212,6 +212,13 @@ def greedy_pick(logits, vocab, bias_all, bias_begin, begin_pos, seq, prompt_len,
               seq.stride(0), int(prompt_len), _ptr(finished), int(eos), int(pad), _ptr(pos_dev), seq.shape[0], _stream())
 
 
+def greedy_pick_timestamps(logits, vocab, bias_all, bias_begin, begin_pos, seq, prompt_len, finished, eos, pad, pos_dev, timestamp_begin,
+                           max_initial_timestamp_index):
+    _abi.call("dwb_greedy_pick_timestamps", _ptr(logits), logits.stride(0), vocab, _ptr(bias_all), _ptr(bias_begin), int(begin_pos), _ptr(seq),
+              seq.stride(0), int(prompt_len), _ptr(finished), int(eos), int(pad), _ptr(pos_dev), seq.shape[0], int(timestamp_begin),
+              -1 if max_initial_timestamp_index is None else int(max_initial_timestamp_index), _stream())
+
+
 def decode_advance(pos_dev, finished, done_at):
     _abi.call("dwb_decode_advance", _ptr(pos_dev), _ptr(finished), finished.numel(), _ptr(done_at), _stream())
 

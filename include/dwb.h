@@ -125,6 +125,12 @@ int dwb_attention_decode(const void* q, int64_t ldq, const void* k_new, const vo
                          const int* pos_dev, float scale, void* stream);
 int dwb_greedy_pick(const float* logits, int64_t ld, int vocab, const float* bias_all, const float* bias_begin, int begin_pos, int64_t* seq,
                     int seq_ld, int prompt_len, int* finished, int64_t eos, int64_t pad, const int* pos_dev, int B, void* stream);
+/* dwb_greedy_pick under Whisper's timestamp rules (return_timestamps=True, the reference's recommended pseudo-labelling mode,
+ * ref:training/README.md:130,148): HF:generation/logits_process.py WhisperTimeStampLogitsProcessor applied after the suppress biases.
+ * timestamp_begin = <|notimestamps|> + 1; max_initial_timestamp_index < 0: no limit. */
+int dwb_greedy_pick_timestamps(const float* logits, int64_t ld, int vocab, const float* bias_all, const float* bias_begin, int begin_pos,
+                               int64_t* seq, int seq_ld, int prompt_len, int* finished, int64_t eos, int64_t pad, const int* pos_dev, int B,
+                               int timestamp_begin, int max_initial_timestamp_index, void* stream);
 int dwb_decode_advance(int* pos_dev, const int* finished, int B, int* done_at, void* stream);
 
 /* ---- label side of the data collator: ref:training/run_distillation.py:460-476 --------------------------------------

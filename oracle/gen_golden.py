@@ -155,7 +155,7 @@ GEN_EN = dict(decoder_start_token_id=501, eos_token_id=502, pad_token_id=500, bo
               no_timestamps_token_id=508, suppress_tokens=None, begin_suppress_tokens=None)
 
 
-def hf_greedy(m, feats, gen_cfg: dict, language, task, eos, **length):
+def hf_greedy(m, feats, gen_cfg: dict, language, task, eos, timestamps=False, **length):
     """Initial tokens from WhisperGenerationMixin's own helpers (HF:models/whisper/generation_whisper.py:1420-1608), then
     GenerationMixin.generate (greedy `_sample`) with HF's suppress processors -- the 4.3x-era contract the reference was written
     against: prompt + generated (+ EOS, pad).  HF 5.x's Whisper wrapper post-processes this (strips prompt / EOS, long-form seek)."""
@@ -163,7 +163,7 @@ def hf_greedy(m, feats, gen_cfg: dict, language, task, eos, **length):
     from transformers.generation import (GenerationMixin, LogitsProcessorList, SuppressTokensAtBeginLogitsProcessor,
                                          SuppressTokensLogitsProcessor)
     g = GenerationConfig(**{k: v for k, v in dict(gen_cfg, eos_token_id=eos).items() if v is not None})
-    g.return_timestamps = False
+    g.return_timestamps = bool(timestamps)
     m._set_language_and_task(language=language, task=task, is_multilingual=None, generation_config=g)
     init = m._retrieve_init_tokens(feats, batch_size=feats.shape[0], generation_config=g, config=m.config,
                                    num_segment_frames=feats.shape[-1], kwargs={})
@@ -173,9 +173,14 @@ def hf_greedy(m, feats, gen_cfg: dict, language, task, eos, **length):
     begin = [eos if t == gen_cfg["eos_token_id"] else t for t in (gen_cfg.get("begin_suppress_tokens") or [])]
     if begin:
         procs.append(SuppressTokensAtBeginLogitsProcessor(begin, begin_index=init.shape[1], device="cpu"))
+    if timestamps:       # HF :1774-1778: the timestamp processor runs after the two suppress processors
+        from transformers.generation import WhisperTimeStampLogitsProcessor
+        procs.append(WhisperTimeStampLogitsProcessor(g, begin_index=init.shape[1]))
     g2 = GenerationConfig(decoder_start_token_id=gen_cfg["decoder_start_token_id"], eos_token_id=eos, pad_token_id=gen_cfg["pad_token_id"],
                           bos_token_id=gen_cfg["bos_token_id"], do_sample=False, num_beams=1, **length)
-    out = GenerationMixin.generate(m, feats, decoder_input_ids=init, logits_processor=LogitsProcessorList(procs), generation_config=g2)
+    plist = LogitsProcessorList(procs)
+    out = GenerationMixin.generate(m, feats, decoder_input_ids=init, logits_processor=plist, generation_config=g2)
+    hf_greedy.last_processors = plist
     return init, out, begin
 
 
@@ -203,7 +208,36 @@ def gen_generate(n_rows=4):
     out = {"transformers_version": np.array(ver), "model_seed": np.array(GEN_MODEL_SEED), "model_std": np.array(GEN_MODEL_STD)}
     NEVER = 509
 
-    def case(name, gen_cfg, language, task, pick_eos, **length):
+    def case(name, gen_cfg, language, task, pick_eos, timestamps=False, **length):
+        if timestamps:      # margins of the PROCESSED scores (the rules are path dependent) along each row's decoded path; golden EOS
+            eos = gen_cfg["eos_token_id"]
+            init, seq, begin = hf_greedy(m, pool, gen_cfg, language, task, eos, timestamps=True, **length)
+            procs, P = hf_greedy.last_processors, init.shape[1]
+            with torch.no_grad():
+                lg = m(input_features=pool, decoder_input_ids=seq[:, :-1]).logits.float()
+            mx = float(lg.abs().max())
+            marg = torch.full((GEN_POOL,), 1e9)
+            for t in range(P, seq.shape[1]):
+                sc = procs(seq[:, :t], lg[:, t - 1].clone())
+                t2 = sc.topk(2, -1).values
+                gap = (t2[:, 0] - t2[:, 1]) / mx
+                alive = ~(seq[:, P:t] == eos).any(dim=1)                      # positions after EOS are padding
+                marg = torch.where(alive, torch.minimum(marg, gap), marg)
+            rows = marg.topk(n_rows).indices.sort().values
+            feats = pool[rows]
+            init2, seq2, begin2 = hf_greedy(m, feats, gen_cfg, language, task, eos, timestamps=True, **length)
+            for r in range(n_rows):
+                a_, b_ = seq2[r].tolist(), seq[rows[r]].tolist()
+                stop = a_.index(eos) + 1 if eos in a_[P:] else len(a_)
+                assert a_[:stop] == b_[:stop], (name, r, a_, b_)
+            out[f"{name}_feats"] = feats.numpy().astype(np.float32)
+            out[f"{name}_init"] = init2.numpy()
+            out[f"{name}_seq"] = seq2.numpy()
+            out[f"{name}_eos"] = np.array(eos)
+            out[f"{name}_begin_suppress"] = np.array(begin2, dtype=np.int64)
+            out[f"{name}_min_rel_margin"] = marg[rows].numpy()
+            print("generate", name, "(timestamps) rows", rows.tolist(), "min rel margin", marg[rows].min().item(), "\n", seq2)
+            return
         init, seq, begin = hf_greedy(m, pool, gen_cfg, language, task, NEVER, **length)
         P = init.shape[1]
         marg, lg = _row_margins(m, pool, seq, P, gen_cfg.get("suppress_tokens"), [NEVER if t == gen_cfg["eos_token_id"] else t for t in (gen_cfg.get("begin_suppress_tokens") or [])])
@@ -234,6 +268,7 @@ def gen_generate(n_rows=4):
     case("A", GEN_MULTI, "fr", "transcribe", True, max_new_tokens=10)          # ref gen_kwargs for multilingual models (:1441-1445)
     case("B", GEN_MULTI, None, None, False, max_length=12)                     # language detection, no task, max_length semantics
     case("C", GEN_EN, None, None, True, max_new_tokens=6)                      # English-only model: <|sot|><|notimestamps|>
+    case("D", dict(GEN_MULTI, max_initial_timestamp_index=1), "en", "transcribe", False, timestamps=True, max_new_tokens=8)   # pseudo-labelling mode
     np.savez_compressed(os.path.join(OUT, "generate_tiny.npz"), **out)
 
 

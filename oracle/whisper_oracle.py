@@ -247,8 +247,38 @@ def model_forward(sd: dict, c: WhisperDims, input_features=None, decoder_input_i
 
 
 @torch.no_grad()
+def timestamp_rules(ids, scores, begin_index, timestamp_begin, eos_token_id, max_initial_timestamp_index=None):
+    """HF:generation/logits_process.py WhisperTimeStampLogitsProcessor.__call__, restated: ids int64 [B, t] (prompt + generated),
+    scores fp32 [B, V] -> processed scores."""
+    s = scores.clone()
+    s[:, timestamp_begin - 1] = -float("inf")                                  # <|notimestamps|>
+    for k in range(ids.shape[0]):
+        seq = ids[k, begin_index:].tolist()
+        last = len(seq) >= 1 and seq[-1] >= timestamp_begin
+        penult = len(seq) < 2 or seq[-2] >= timestamp_begin
+        if last:
+            if penult:
+                s[k, timestamp_begin:] = -float("inf")                         # a closed pair: text next
+            else:
+                s[k, :eos_token_id] = -float("inf")                            # text then one timestamp: no text below EOS
+        ts = [t for t in seq if t >= timestamp_begin]
+        if ts:
+            lo = ts[-1] if (last and not penult) else ts[-1] + 1               # never decrease, never repeat <|0.00|>
+            s[k, timestamp_begin:lo] = -float("inf")
+    if ids.shape[1] == begin_index:
+        s[:, :timestamp_begin] = -float("inf")
+        if max_initial_timestamp_index is not None:
+            s[:, timestamp_begin + max_initial_timestamp_index + 1:] = -float("inf")
+    lp = F.log_softmax(s.float(), dim=-1)
+    for k in range(ids.shape[0]):
+        if lp[k, timestamp_begin:].logsumexp(dim=-1) > lp[k, :timestamp_begin].max():
+            s[k, :timestamp_begin] = -float("inf")
+    return s
+
+
+@torch.no_grad()
 def greedy_generate(sd: dict, c: WhisperDims, input_features, prompt, eos_token_id, pad_token_id, limit, suppress_tokens=None,
-                    begin_suppress_tokens=None):
+                    begin_suppress_tokens=None, timestamp_begin=None, max_initial_timestamp_index=None):
     """Greedy search as HF:generation/utils.py `_sample` runs it for Whisper (do_sample False, one beam) with the two logits
     processors of HF:models/whisper/generation_whisper.py:1774-1800: `suppress_tokens` at every step, `begin_suppress_tokens` at
     the first generated position (begin_index = prompt length).  Finished rows emit pad; stops when every row has emitted EOS or
@@ -265,6 +295,8 @@ def greedy_generate(sd: dict, c: WhisperDims, input_features, prompt, eos_token_
             logits[:, list(suppress_tokens)] = -float("inf")
         if begin_suppress_tokens and ids.shape[1] == P:
             logits[:, list(begin_suppress_tokens)] = -float("inf")
+        if timestamp_begin is not None:                                        # return_timestamps=True (HF :1774-1778 order)
+            logits = timestamp_rules(ids, logits, P, timestamp_begin, eos_token_id, max_initial_timestamp_index)
         nxt = logits.argmax(dim=-1)
         nxt = torch.where(unfinished, nxt, torch.full_like(nxt, pad_token_id))
         ids = torch.cat([ids, nxt[:, None]], dim=1)

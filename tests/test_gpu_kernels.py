@@ -391,3 +391,34 @@ def test_device_collator_matches_reference_collator_semantics():
     b3 = coll2([{"input_features": want[i], "labels": r} for i, r in enumerate(rows)])
     d3, l3 = wo.collate_labels(rows, pad, sot)
     assert torch.equal(b3["labels"].cpu(), l3) and torch.equal(b3["decoder_input_ids"].cpu(), d3)
+
+
+def test_greedy_pick_with_timestamp_rules_matches_hf_processor_semantics():
+    """dwb_greedy_pick_timestamps against oracle.timestamp_rules (== HF's WhisperTimeStampLogitsProcessor, pinned on CPU by
+    tests/test_oracle.py) + suppress biases, on crafted prefixes covering every rule."""
+    from distil_whisper_b200 import ops
+    from oracle import whisper_oracle as wo
+    from tests.test_oracle import _timestamp_cases
+    V, ld, ts_begin, eos, begin = 140, 144, 130, 120, 3
+    for max_init in (None, 1):
+        for ids, logits in _timestamp_cases(6, V, ts_begin, eos, begin, seed=3):
+            B, t = ids.shape
+            suppress, begin_suppress = [2, 11, 131], [eos, 7]
+            sc = logits.clone()
+            sc[:, suppress] = -float("inf")
+            if t == begin:
+                sc[:, begin_suppress] = -float("inf")
+            want = wo.timestamp_rules(ids, sc, begin, ts_begin, eos, max_init).argmax(-1)
+            buf = torch.full((B, ld), 1e9, device="cuda")
+            buf[:, :V] = logits.cuda()
+            bias_all = torch.zeros(V, device="cuda")
+            bias_all[suppress] = float("-inf")
+            bias_begin = torch.zeros(V, device="cuda")
+            bias_begin[begin_suppress] = float("-inf")
+            seq = torch.full((B, t + 2), 99, dtype=torch.int64, device="cuda")
+            seq[:, :t] = ids.cuda()
+            finished = torch.zeros(B, dtype=torch.int32, device="cuda")
+            pos = torch.tensor([t - 1], dtype=torch.int32, device="cuda")
+            ops.greedy_pick_timestamps(buf, V, bias_all, bias_begin, begin, seq, begin, finished, eos, 99, pos, ts_begin, max_init)
+            assert torch.equal(seq[:, t].cpu(), want), (max_init, ids[0].tolist(), seq[:, t].cpu(), want)
+            assert torch.equal(finished.cpu().bool(), want == eos)

@@ -270,8 +270,8 @@ def test_greedy_generate_follows_the_oracle_argmax():
     assert out3.shape[1] <= 5 and (out3[:, 0] == sc.decoder_start_token_id).all() and m.training
     with pytest.raises(NotImplementedError):
         m.generate(feats.cuda(), num_beams=4)
-    with pytest.raises(NotImplementedError):
-        m.generate(feats.cuda(), return_timestamps=True)
+    with pytest.raises(ValueError):
+        m.generate(feats.cuda(), return_timestamps=True)          # no no_timestamps_token_id in the generation config
 
 
 def _tiny_pair(freeze_encoder=True, lr=1e-3):
@@ -398,9 +398,11 @@ def test_kv_cached_generate_reproduces_hf_token_ids(golden_dir, dtype):
     g = np.load(os.path.join(golden_dir, "generate_tiny.npz"))
     sc = wo.PRESETS["tiny-student"]
     m = _build(sc, wo.init_state_dict(sc, int(g["model_seed"]), std=float(g["model_std"])), dtype=dtype)
-    cases = {"A": (GEN_MULTI, dict(language="fr", task="transcribe", max_new_tokens=10)),
-             "B": (GEN_MULTI, dict(max_length=12)),
-             "C": (GEN_EN, dict(max_new_tokens=6))}
+    cases = {"A": (GEN_MULTI, dict(language="fr", task="transcribe", max_new_tokens=10, return_timestamps=False)),
+             "B": (GEN_MULTI, dict(max_length=12, return_timestamps=False)),
+             "C": (GEN_EN, dict(max_new_tokens=6, return_timestamps=False)),
+             # the reference's recommended pseudo-labelling mode: timestamp rules inside the token pick
+             "D": (dict(GEN_MULTI, max_initial_timestamp_index=1), dict(language="en", task="transcribe", max_new_tokens=8, return_timestamps=True))}
     for name, (cfg, kw) in cases.items():
         eos = int(g[f"{name}_eos"])
         gen = dict(cfg, eos_token_id=eos)
@@ -408,13 +410,13 @@ def test_kv_cached_generate_reproduces_hf_token_ids(golden_dir, dtype):
             gen["begin_suppress_tokens"] = [int(t) for t in g[f"{name}_begin_suppress"]]
         m.generation_config = gen
         feats = torch.from_numpy(g[f"{name}_feats"]).cuda()
-        out = m.generate(feats, num_beams=1, return_timestamps=False, **kw)
+        out = m.generate(feats, num_beams=1, **kw)
         ref = torch.from_numpy(g[f"{name}_seq"])
         assert out.dtype == torch.long and tuple(out.shape) == tuple(ref.shape), (name, out.shape, ref.shape)
         assert torch.equal(out.cpu(), ref), (name, out.cpu(), ref)
         # a second call on the same session (graph reuse, weights unchanged) and a sub-batch give the same rows
-        assert torch.equal(m.generate(feats, num_beams=1, return_timestamps=False, **kw).cpu(), ref)
-        sub = m.generate(feats[1:3], num_beams=1, return_timestamps=False, **kw).cpu()
+        assert torch.equal(m.generate(feats, num_beams=1, **kw).cpu(), ref)
+        sub = m.generate(feats[1:3], num_beams=1, **kw).cpu()
         for r in range(2):
             row, want = sub[r].tolist(), ref[1 + r].tolist()
             n = min(len(row), len(want))

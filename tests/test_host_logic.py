@@ -106,9 +106,11 @@ def test_generate_rejects_unsupported_decoding_modes_before_touching_the_device(
     from distil_whisper_b200.modeling import DistilWhisperB200ForConditionalGeneration
     m = DistilWhisperB200ForConditionalGeneration(wo.PRESETS["tiny-student"].to_dict())
     feats = torch.zeros((1, 80, 100))
-    for kw in (dict(num_beams=4), dict(do_sample=True), dict(return_timestamps=True), dict(forced_decoder_ids=[(1, 2)])):
+    for kw in (dict(num_beams=4), dict(do_sample=True), dict(forced_decoder_ids=[(1, 2)]), dict(prompt_ids=[1, 2]), dict(made_up_flag=1)):
         with pytest.raises(NotImplementedError):
             m.generate(feats, **kw)
+    with pytest.raises(ValueError):                  # timestamps need the generation config's no_timestamps_token_id (as in HF)
+        m.generate(feats, return_timestamps=True)
 
 
 def test_pad_label_rows_matches_tokenizer_pad_semantics():

@@ -98,7 +98,8 @@ GEN_EN = dict(decoder_start_token_id=501, eos_token_id=502, pad_token_id=500, bo
               no_timestamps_token_id=508, suppress_tokens=None, begin_suppress_tokens=None)
 GEN_CASES = {"A": (GEN_MULTI, dict(language="fr", task="transcribe", max_new_tokens=10)),
              "B": (GEN_MULTI, dict(max_length=12)),
-             "C": (GEN_EN, dict(max_new_tokens=6))}
+             "C": (GEN_EN, dict(max_new_tokens=6)),
+             "D": (dict(GEN_MULTI, max_initial_timestamp_index=1), dict(language="en", task="transcribe", max_new_tokens=8, return_timestamps=True))}
 
 
 def test_oracle_greedy_generate_reproduces_hf_golden(golden_dir):
@@ -112,8 +113,10 @@ def test_oracle_greedy_generate_reproduces_hf_golden(golden_dir):
     for name, (cfg, kw) in GEN_CASES.items():
         feats, init, seq = torch.from_numpy(g[f"{name}_feats"]), torch.from_numpy(g[f"{name}_init"]), g[f"{name}_seq"]
         limit = kw["max_length"] if "max_length" in kw else init.shape[1] + kw["max_new_tokens"]
+        ts = dict(timestamp_begin=cfg["no_timestamps_token_id"] + 1, max_initial_timestamp_index=cfg.get("max_initial_timestamp_index")) \
+            if kw.get("return_timestamps") else {}
         out = wo.greedy_generate(sd, sc, feats, init, int(g[f"{name}_eos"]), cfg["pad_token_id"], limit, cfg.get("suppress_tokens"),
-                                 [int(t) for t in g[f"{name}_begin_suppress"]])
+                                 [int(t) for t in g[f"{name}_begin_suppress"]], **ts)
         assert out.shape == seq.shape and (out.numpy() == seq).all(), (name, out, seq)
         assert float(g[f"{name}_min_rel_margin"].min()) > 0.02       # the fixture rows were chosen for decisive arg-maxima
 
@@ -137,6 +140,9 @@ def test_initial_tokens_follow_hf_retrieve_init_tokens(golden_dir):
     b = generation.initial_tokens(model, GEN_MULTI, None, None, False, detect=lambda: det)
     assert b == g["B_init"].tolist()
     assert generation.initial_tokens(model, GEN_EN, None, None, False, None) == [g["C_init"][0].tolist()]
+    assert generation.initial_tokens(model, GEN_MULTI, "en", "transcribe", True, None) == [g["D_init"][0].tolist()]     # no <|notimestamps|>
+    forced_nots = dict(GEN_MULTI, forced_decoder_ids=[[1, 504], [2, 507], [3, 508]])
+    assert generation.initial_tokens(model, forced_nots, None, None, True, None) == [[501, 504, 507]]
     forced = dict(GEN_MULTI, forced_decoder_ids=[[1, 504], [2, 507], [3, 508]])
     assert generation.initial_tokens(model, forced, None, None, False, None) == [[501, 504, 507, 508]]
     with pytest.raises(ValueError):
@@ -145,3 +151,42 @@ def test_initial_tokens_follow_hf_retrieve_init_tokens(golden_dir):
         generation.initial_tokens(model, GEN_MULTI, "xx", None, False, None)       # unknown language
     with pytest.raises(ValueError):
         generation.initial_tokens(model, GEN_MULTI, "en", "summarise", False, None)
+
+
+def _timestamp_cases(B, V, ts_begin, eos, begin, seed):
+    """Random logits + crafted prefixes covering every branch of the timestamp rules."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn((B, V), generator=g) * 2.0
+    logits[:, ts_begin:] += torch.randn((B, 1), generator=g) * 2.0            # sometimes the timestamps outweigh the text
+    t = lambda k: ts_begin + k                                                 # noqa: E731
+    bodies = [[], [t(0)], [t(0), 7], [t(0), 7, t(2)], [t(0), 7, t(2), t(2)], [t(0), 7, t(2), t(2), 9], [t(1), 3, 4, t(3)], [t(0), t(0), 5, 6],
+              [t(0), 5, t(4), t(4), 6, t(5)], [t(2), 11]]
+    out = []
+    for body in bodies:
+        ids = torch.full((B, begin + len(body)), 5, dtype=torch.long)
+        ids[:, :begin] = torch.arange(begin) + eos + 1                          # "initial tokens"
+        if body:
+            ids[:, begin:] = torch.tensor(body)
+        out.append((ids, logits.clone()))
+    return out
+
+
+def test_oracle_timestamp_rules_match_hf_processor():
+    """oracle.timestamp_rules == transformers' WhisperTimeStampLogitsProcessor on crafted prefixes (pins the restatement the
+    GPU pick kernel is checked against)."""
+    import types
+
+    import pytest
+    import torch
+    transformers = pytest.importorskip("transformers")
+    from transformers.generation import WhisperTimeStampLogitsProcessor
+    from oracle import whisper_oracle as wo
+    V, ts_begin, eos, begin = 140, 130, 120, 3
+    for max_init in (None, 1):
+        cfg = types.SimpleNamespace(no_timestamps_token_id=ts_begin - 1, eos_token_id=eos, bos_token_id=eos, max_initial_timestamp_index=max_init)
+        proc = WhisperTimeStampLogitsProcessor(cfg, begin_index=begin)
+        for ids, logits in _timestamp_cases(6, V, ts_begin, eos, begin, seed=3):
+            want = proc(ids, logits.clone())
+            got = wo.timestamp_rules(ids, logits.clone(), begin, ts_begin, eos, max_init)
+            assert torch.equal(torch.isinf(want), torch.isinf(got)) and torch.equal(want.argmax(-1), got.argmax(-1))
