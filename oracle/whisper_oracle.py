@@ -276,6 +276,25 @@ def timestamp_rules(ids, scores, begin_index, timestamp_begin, eos_token_id, max
     return s
 
 
+def synthetic_timestamp_cases(B, V, ts_begin, eos, begin, seed):
+    """Random logits + crafted prefixes covering every branch of the timestamp rules."""
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn((B, V), generator=g) * 2.0
+    logits[:, ts_begin:] += torch.randn((B, 1), generator=g) * 2.0            # sometimes the timestamps outweigh the text
+    t = lambda k: ts_begin + k                                                 # noqa: E731
+    bodies = [[], [t(0)], [t(0), 7], [t(0), 7, t(2)], [t(0), 7, t(2), t(2)], [t(0), 7, t(2), t(2), 9], [t(1), 3, 4, t(3)], [t(0), t(0), 5, 6],
+              [t(0), 5, t(4), t(4), 6, t(5)], [t(2), 11]]
+    out = []
+    for body in bodies:
+        ids = torch.full((B, begin + len(body)), 5, dtype=torch.long)
+        ids[:, :begin] = torch.arange(begin) + eos + 1                          # "initial tokens"
+        if body:
+            ids[:, begin:] = torch.tensor(body)
+        out.append((ids, logits.clone()))
+    return out
+
+
+
 @torch.no_grad()
 def greedy_generate(sd: dict, c: WhisperDims, input_features, prompt, eos_token_id, pad_token_id, limit, suppress_tokens=None,
                     begin_suppress_tokens=None, timestamp_begin=None, max_initial_timestamp_index=None):

@@ -398,10 +398,9 @@ def test_greedy_pick_with_timestamp_rules_matches_hf_processor_semantics():
     tests/test_oracle.py) + suppress biases, on crafted prefixes covering every rule."""
     from distil_whisper_b200 import ops
     from oracle import whisper_oracle as wo
-    from tests.test_oracle import _timestamp_cases
     V, ld, ts_begin, eos, begin = 140, 144, 130, 120, 3
     for max_init in (None, 1):
-        for ids, logits in _timestamp_cases(6, V, ts_begin, eos, begin, seed=3):
+        for ids, logits in wo.synthetic_timestamp_cases(6, V, ts_begin, eos, begin, seed=3):
             B, t = ids.shape
             suppress, begin_suppress = [2, 11, 131], [eos, 7]
             sc = logits.clone()

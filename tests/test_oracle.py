@@ -153,25 +153,6 @@ def test_initial_tokens_follow_hf_retrieve_init_tokens(golden_dir):
         generation.initial_tokens(model, GEN_MULTI, "en", "summarise", False, None)
 
 
-def _timestamp_cases(B, V, ts_begin, eos, begin, seed):
-    """Random logits + crafted prefixes covering every branch of the timestamp rules."""
-    import torch
-    g = torch.Generator().manual_seed(seed)
-    logits = torch.randn((B, V), generator=g) * 2.0
-    logits[:, ts_begin:] += torch.randn((B, 1), generator=g) * 2.0            # sometimes the timestamps outweigh the text
-    t = lambda k: ts_begin + k                                                 # noqa: E731
-    bodies = [[], [t(0)], [t(0), 7], [t(0), 7, t(2)], [t(0), 7, t(2), t(2)], [t(0), 7, t(2), t(2), 9], [t(1), 3, 4, t(3)], [t(0), t(0), 5, 6],
-              [t(0), 5, t(4), t(4), 6, t(5)], [t(2), 11]]
-    out = []
-    for body in bodies:
-        ids = torch.full((B, begin + len(body)), 5, dtype=torch.long)
-        ids[:, :begin] = torch.arange(begin) + eos + 1                          # "initial tokens"
-        if body:
-            ids[:, begin:] = torch.tensor(body)
-        out.append((ids, logits.clone()))
-    return out
-
-
 def test_oracle_timestamp_rules_match_hf_processor():
     """oracle.timestamp_rules == transformers' WhisperTimeStampLogitsProcessor on crafted prefixes (pins the restatement the
     GPU pick kernel is checked against)."""
@@ -186,7 +167,7 @@ def test_oracle_timestamp_rules_match_hf_processor():
     for max_init in (None, 1):
         cfg = types.SimpleNamespace(no_timestamps_token_id=ts_begin - 1, eos_token_id=eos, bos_token_id=eos, max_initial_timestamp_index=max_init)
         proc = WhisperTimeStampLogitsProcessor(cfg, begin_index=begin)
-        for ids, logits in _timestamp_cases(6, V, ts_begin, eos, begin, seed=3):
+        for ids, logits in wo.synthetic_timestamp_cases(6, V, ts_begin, eos, begin, seed=3):
             want = proc(ids, logits.clone())
             got = wo.timestamp_rules(ids, logits.clone(), begin, ts_begin, eos, max_init)
             assert torch.equal(torch.isinf(want), torch.isinf(got)) and torch.equal(want.argmax(-1), got.argmax(-1))
