@@ -54,6 +54,7 @@ SIGNATURES = {
     "dwb_kd_loss_workspace_bytes": (_l, [_i]),
     "dwb_kd_loss": (_i, [_p, _p, _l, _p, _i, _i, _f, _f, _f, _p, _p, _l, _p, _p]),
     "dwb_set_tail_grid": (_i, [_i]),
+    "dwb_allreduce_symm": (_i, [_p, _p, _i, _i, _l, _i, _p]),
     "dwb_grad_sumsq": (_i, [_p, _l, _p, _p]),
     "dwb_adamw_step": (_i, [_p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _i, _p, _f, _f, _i, _p]),
     "dwb_logmel_plan_create": (_i, [_p, _i, _i, C.POINTER(_p)]),

@@ -12,6 +12,37 @@ from torch import nn
 from . import ops
 
 
+def _symmetric_grad_buffer(total: int, dev):
+    """The flat gradient buffer in symmetric memory (every rank maps every peer's buffer), so that the gradient all-reduce can be
+    the small-footprint peer-memory kernel dwb_allreduce_symm instead of NCCL.  Collective: every rank must call it at the same
+    point (FusedAdamW construction).  Returns (tensor, handle) or (None, None) when not applicable / not available -- then the
+    buffer is an ordinary tensor and the all-reduce goes through NCCL.  DWB_SYMM_ALLREDUCE=0 disables it."""
+    import os
+    import torch.distributed as dist
+    if os.environ.get("DWB_SYMM_ALLREDUCE", "1") == "0" or dev.type != "cuda":
+        return None, None
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and dist.get_backend() == "nccl"):
+        return None, None
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        group = dist.group.WORLD
+        if hasattr(symm_mem, "enable_symm_mem_for_group"):
+            try:
+                symm_mem.enable_symm_mem_for_group(group.group_name)
+            except Exception:  # noqa: BLE001  (newer versions enable lazily)
+                pass
+        buf = symm_mem.empty(total, dtype=torch.float32, device=dev)
+        hdl = symm_mem.rendezvous(buf, group)
+        buf.zero_()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        return buf, hdl
+    except Exception as ex:  # noqa: BLE001
+        import warnings
+        warnings.warn(f"symmetric-memory gradient buffer unavailable ({type(ex).__name__}: {ex}); the all-reduce uses NCCL")
+        return None, None
+
+
 def get_parameter_names(model, forbidden_layer_types, forbidden_module=None):
     """Same contract as ref:training/run_distillation.py:760-778 (names outside forbidden layer types / modules)."""
     result = []
@@ -56,7 +87,9 @@ class FlatBuffers:
                 total += (p.numel() + 3) // 4 * 4
             self.groups.append((start, total - start, list(g)))
         self.data = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad, self.symm = _symmetric_grad_buffer(total, dev)
+        if self.grad is None:
+            self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
         with torch.no_grad():
             for p, off in layout:
                 view = self.data[off:off + p.numel()].view(p.shape)
@@ -79,9 +112,33 @@ class FlatBuffers:
         the optimiser's grad_scale).  ref: implicit DDP all-reduce inside accelerator.backward, :1609."""
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
+            if self.symm is not None and group is None:
+                self._all_reduce_symm()
+            else:
+                dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
             return dist.get_world_size(group)
         return 1
+
+    def _all_reduce_symm(self):
+        """Peer-memory all-reduce (csrc/collective.cu): barrier (every rank's gradient is complete and visible), one kernel in which
+        rank r sums slice r of the N buffers -- inside the NVSwitch when the buffer has a multicast mapping -- and writes the sum
+        into all of them, barrier (every slice is written).  Runs on the current stream; a few no-smem CTAs."""
+        import ctypes as C
+        import os
+        from . import _abi
+        h, n = self.symm, self.grad.numel()
+        world, rank = h.world_size, h.rank
+        off = int(getattr(h, "offset", 0) or 0)
+        mc = 0 if os.environ.get("DWB_SYMM_NO_MC", "0") == "1" else int(getattr(h, "multicast_ptr", 0) or 0)
+        if not hasattr(self, "_symm_peers"):
+            peers = [h.get_buffer(r, (n,), torch.float32) for r in range(world)]
+            self._symm_peer_tensors = peers                     # keep the mappings alive
+            self._symm_peers = (C.c_void_p * world)(*[C.c_void_p(t.data_ptr()) for t in peers])
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        h.barrier(channel=0)
+        _abi.call("dwb_allreduce_symm", C.c_void_p(mc + off) if mc else None, self._symm_peers, rank, world, n,
+                  int(os.environ.get("DWB_SYMM_CTAS", "32")), stream)
+        h.barrier(channel=1)
 
 
 class FusedAdamW(torch.optim.Optimizer):

@@ -161,6 +161,12 @@ int dwb_adamw_step(float* p, float* g, float* m, float* v, void* p_bf16, int64_t
                    float weight_decay, int step, const float* grad_sumsq, float max_grad_norm, float grad_scale, int zero_grad,
                    void* stream);
 
+/* ---- the gradient all-reduce over symmetric (peer-mapped) memory: ref:training/run_distillation.py:1609 (DDP's implicit all-reduce) ---
+ * In place, "two-shot": rank r sums slice r of the N copies (NVSwitch multimem.ld_reduce when multicast_ptr != NULL, else plain loads
+ * through peer_ptrs[world]) and writes the sum into slice r of all N buffers.  The caller provides the cross-rank barriers before and
+ * after (torch.distributed._symmetric_memory handle).  A few no-smem CTAs (max_ctas, default 32): co-resident with the GEMM kernels. */
+int dwb_allreduce_symm(void* multicast_ptr, const void* const* peer_ptrs, int rank, int world, int64_t n, int max_ctas, void* stream);
+
 /* ---- log-mel feature extractor: HF:models/whisper/feature_extraction_whisper.py:135-164 ------------------------
  * plan: mel filter bank [201, n_mels] fp32 on the HOST (HF:audio_utils.py:453-544) -> device tables.
  * wav [B, 480000] fp32 -> out [B, n_mels, 3000] fp32.  One 8-CTA cluster per utterance. */
