@@ -62,11 +62,15 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        # the recipe's period (B200_PROFILING.md: -lms 200); DWB_BENCH_SMI_MS overrides for A/B runs (0 = no sampling)
+        self.period_ms = int(os.environ.get("DWB_BENCH_SMI_MS", "200"))
 
     def start(self):
         try:
+            if self.period_ms <= 0:
+                return
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", str(self.period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:  # noqa: BLE001
             self.proc = None
@@ -224,12 +228,19 @@ def measure_kd_step(variant, steps, warmup, rank, local, world, use_graph=True, 
     res["sec"] = sec
     res["launch_mode"] = "eager" if trainer is None else trainer.describe()
     if trainer is not None and full:
-        # exposed part of the tail (all-reduce + clip + AdamW): the same replays with the tail switched off, subtracted
-        n2 = max(3, steps // 2)
-        sec_notail = _timed(lambda: trainer.step(None, tail=False), n2, world)
-        opt.flat.grad.zero_()
-        res["exposed_comm_ms"] = {"value": (sec - sec_notail) * 1e3, "ms_per_step_without_tail": sec_notail * 1e3,
-                                  "what": "ms_per_step minus the same graph replays with all-reduce + clip + AdamW switched off"}
+        # exposed part of the tail (all-reduce + clip + AdamW): CUDA events inside the trainer -- how long the main stream sat between
+        # the end of graph E and the start of graph D waiting for the previous step's tail; the tail's own duration on its stream
+        n2 = max(4, steps // 2)
+        trainer.profile = []
+        _timed(lambda: trainer.step(None), n2, world, finish)
+        prof, trainer.profile = trainer.profile[1:], None
+        if prof:
+            res["exposed_comm_ms"] = {"value": sum(p[1].elapsed_time(p[5]) for p in prof) / len(prof),
+                                      "tail_ms_on_side_stream": sum(p[3].elapsed_time(p[4]) for p in prof) / len(prof),
+                                      "graph_E_ms": sum(p[0].elapsed_time(p[1]) for p in prof) / len(prof),
+                                      "graph_D_ms": sum(p[5].elapsed_time(p[2]) for p in prof) / len(prof),
+                                      "what": "main-stream wait between the end of graph E and the start of graph D (CUDA events), i.e. the part of "
+                                              "all-reduce + clip + AdamW of the previous step that graph E did not cover; max over ranks not taken"}
     if full:
         # live GEMM roofline: the same K steps launched eagerly with a CUDA-event pair around every tcgen05 GEMM launch
         # (kernels inside a replayed graph cannot be bracketed by events); the library counts its own kernel launches

@@ -226,6 +226,7 @@ class PipelinedTrainer:
         self.bwd_done, self.tail_done = torch.cuda.Event(), torch.cuda.Event()
         self._tail_pending = False
         self._micro = 0
+        self.profile = None                   # set to [] to collect (E start, E end, D end, tail start, tail end, D start) CUDA events per step
         self.g_enc = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_enc):
             self.pre = step.encode_frozen(self.static_batch["input_features"])
@@ -247,21 +248,37 @@ class PipelinedTrainer:
         if batch is not None:
             for k, dst in self.static_batch.items():
                 dst.copy_(batch[k], non_blocking=True)
+        ev = None
+        if self.profile is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+            ev[0].record(main)
         if self.g_enc is not None:
             self.g_enc.replay()
+        if ev:
+            ev[1].record(main)
         if self._tail_pending:                # D reads the weights the previous optimiser step writes and adds into the gradients it zeroes
             main.wait_event(self.tail_done)
             self._tail_pending = False
+        if ev:
+            ev[5].record(main)                # E end (ev[1]) -> here = time the main stream waited for the previous tail
         self.g_dec.replay()
+        if ev:
+            ev[2].record(main)
         self._micro += 1
         run_tail = (self._micro % self.accum == 0) if tail is None else tail
         if run_tail and not self.overlap:
+            if ev:
+                ev[3].record(main)
             self.opt.all_reduce_gradients(self.group)
             self.opt.step()
+            if ev:
+                ev[4].record(main)
         elif run_tail:
             self.bwd_done.record(main)
             with torch.cuda.stream(self.side):
                 self.side.wait_event(self.bwd_done)
+                if ev:
+                    ev[3].record(self.side)
                 with engine.nvtx_range("dwb.grad_all_reduce"):
                     self.opt.all_reduce_gradients(self.group)
                 with engine.nvtx_range("dwb.clip_adamw"):
@@ -270,8 +287,12 @@ class PipelinedTrainer:
                         self.opt.step()
                     finally:
                         self._abi.call("dwb_set_tail_grid", 0)
+                if ev:
+                    ev[4].record(self.side)
                 self.tail_done.record(self.side)
             self._tail_pending = True
+        if ev and run_tail:
+            self.profile.append(ev)
         return self.loss
 
     def flush(self):

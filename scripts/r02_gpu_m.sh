@@ -11,8 +11,8 @@ except Exception as e:
     print(sys.argv[1], "FAILED", e); print(open("gpurun_out/r02m_tmp.err").read()[-800:])
 PY
 }
-run DWB_TAIL_OVERLAP=1
-run DWB_TAIL_OVERLAP=0
-run DWB_TAIL_OVERLAP=1 NCCL_MAX_CTAS=4
-run DWB_TAIL_OVERLAP=1 NCCL_MAX_CTAS=16 NCCL_MIN_CTAS=16
-run DWB_TAIL_OVERLAP=1
+run DWB_SYMM_ALLREDUCE=1
+run DWB_SYMM_ALLREDUCE=0
+run DWB_SYMM_ALLREDUCE=1 DWB_SYMM_CTAS=8
+run DWB_SYMM_ALLREDUCE=1 DWB_SYMM_CTAS=64
+run DWB_SYMM_ALLREDUCE=1 DWB_TAIL_OVERLAP=0
