@@ -42,6 +42,7 @@ SIGNATURES = {
     "dwb_col2im_conv2_gelu_bwd": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "dwb_embed_fwd": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p]),
     "dwb_embed_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "dwb_gemm_skinny_bf16": (_i, [_p, _l, _p, _l, _p, _l, _i, _i, _i, _i, _p, _i, _p]),
     "dwb_embed_decode": (_i, [_p, _i, _p, _p, _p, _i, _p, _i, _i, _i, _p]),
     "dwb_attention_decode": (_i, [_p, _l, _p, _p, _l, _p, _p, _l, _i, _p, _l, _i, _i, _i, _i, _p, _f, _p]),
     "dwb_greedy_pick": (_i, [_p, _l, _i, _p, _p, _i, _p, _i, _i, _p, _l, _l, _p, _i, _p]),

@@ -110,12 +110,29 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(const bf16* __r
   const float inv = 1.f / (s_red[0] + s_red[1] + s_red[2] + s_red[3]);
   float a0 = 0.f, a1 = 0.f;
   int k = warp;
-  for (; k + 3 * (AD_THREADS / 32) < len; k += 4 * (AD_THREADS / 32)) {     // four independent 128 B requests in flight per warp
+  constexpr int NW = AD_THREADS / 32, UNR = 16;
+  for (; k + (UNR - 1) * NW < len; k += UNR * NW) {       // 16 independent 128 B requests in flight per warp: the loop is latency-bound
+    uint32_t u[UNR];
+    float pr[UNR];
+#pragma unroll
+    for (int i = 0; i < UNR; ++i) {
+      const int kk = k + i * NW;
+      u[i] = *reinterpret_cast<const uint32_t*>(vc + (int64_t)kk * ld_cache + 2 * lane);
+      pr[i] = s_p[kk];
+    }
+#pragma unroll
+    for (int i = 0; i < UNR; ++i) {
+      const float2 f = unpack_bf16x2(u[i]);
+      a0 = fmaf(pr[i], f.x, a0);
+      a1 = fmaf(pr[i], f.y, a1);
+    }
+  }
+  for (; k + 3 * NW < len; k += 4 * NW) {
     uint32_t u[4];
     float pr[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int kk = k + i * (AD_THREADS / 32);
+      const int kk = k + i * NW;
       u[i] = *reinterpret_cast<const uint32_t*>(vc + (int64_t)kk * ld_cache + 2 * lane);
       pr[i] = s_p[kk];
     }
@@ -126,7 +143,7 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(const bf16* __r
       a1 = fmaf(pr[i], f.y, a1);
     }
   }
-  for (; k < len; k += AD_THREADS / 32) {
+  for (; k < len; k += NW) {
     const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vc + (int64_t)k * ld_cache + 2 * lane));
     const float pr = s_p[k];
     a0 = fmaf(pr, f.x, a0);
@@ -139,6 +156,84 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(const bf16* __r
     const float r0 = (s_acc[0][2 * tid] + s_acc[1][2 * tid]) + (s_acc[2][2 * tid] + s_acc[3][2 * tid]);
     const float r1 = (s_acc[0][2 * tid + 1] + s_acc[1][2 * tid + 1]) + (s_acc[2][2 * tid + 1] + s_acc[3][2 * tid + 1]);
     *reinterpret_cast<uint32_t*>(o + (int64_t)b * ldo + h * 64 + 2 * tid) = pack_bf16x2(r0 * inv, r1 * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Skinny GEMM for the decode step: C[M, N] = act(X[M, K] . W[N, K]^T + bias) with M = the batch (16 .. 64 rows).  The projection is
+// weight-bandwidth bound (every weight is used by M rows only): the persistent 128-row tcgen05 tiles give such a problem 10 - 40 CTAs
+// and 11 - 14 us; here every warp owns 8 output columns (N / 8 warps = 160 - 640 CTAs of one warp), streams its 8 weight rows once from
+// HBM with four k-steps of loads in flight, takes the activations through L1 (all warps read the same X), and multiplies with
+// mma.sync.m16n8k16 (bf16, fp32 accumulate).  Whisper decoder projections at batch 32: ~3 us.
+__device__ __forceinline__ void mma_m16n8k16_bf16(float* c, const uint32_t* a, const uint32_t* b) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int MT>      // 16-row tiles of X: M = 16 * MT
+__global__ void __launch_bounds__(32) gemm_skinny_kernel(const bf16* __restrict__ x, int64_t ldx, const bf16* __restrict__ w, int64_t ldw,
+                                                        const float* __restrict__ bias, void* __restrict__ c, int64_t ldc, int c_f32,
+                                                        int N, int K, int act) {
+  const int lane = threadIdx.x, g = lane >> 2, t = lane & 3;
+  const int n0 = blockIdx.x * 8;
+  if (n0 >= N) return;
+  float acc[MT][4];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f; }
+  const bf16* wrow = w + (int64_t)(n0 + g) * ldw + 2 * t;            // B fragment: column n0 + g, k = k0 + 2t (+1), k0 + 8 + 2t (+1)
+  const bf16* xrow = x + (int64_t)g * ldx + 2 * t;                   // A fragment rows g, g + 8 of each 16-row tile
+  constexpr int UNR = 4;
+  int k0 = 0;
+  for (; k0 + 16 * UNR <= K; k0 += 16 * UNR) {
+    uint32_t b[UNR][2], a[UNR][MT][4];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int kk = k0 + 16 * u;
+      b[u][0] = *reinterpret_cast<const uint32_t*>(wrow + kk);
+      b[u][1] = *reinterpret_cast<const uint32_t*>(wrow + kk + 8);
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const bf16* xr = xrow + (int64_t)(16 * m) * ldx + kk;
+        a[u][m][0] = *reinterpret_cast<const uint32_t*>(xr);
+        a[u][m][1] = *reinterpret_cast<const uint32_t*>(xr + 8 * ldx);
+        a[u][m][2] = *reinterpret_cast<const uint32_t*>(xr + 8);
+        a[u][m][3] = *reinterpret_cast<const uint32_t*>(xr + 8 * ldx + 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+#pragma unroll
+      for (int m = 0; m < MT; ++m) mma_m16n8k16_bf16(acc[m], a[u][m], b[u]);
+  }
+  for (; k0 < K; k0 += 16) {
+    uint32_t b[2];
+    b[0] = *reinterpret_cast<const uint32_t*>(wrow + k0);
+    b[1] = *reinterpret_cast<const uint32_t*>(wrow + k0 + 8);
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      const bf16* xr = xrow + (int64_t)(16 * m) * ldx + k0;
+      uint32_t a[4];
+      a[0] = *reinterpret_cast<const uint32_t*>(xr);
+      a[1] = *reinterpret_cast<const uint32_t*>(xr + 8 * ldx);
+      a[2] = *reinterpret_cast<const uint32_t*>(xr + 8);
+      a[3] = *reinterpret_cast<const uint32_t*>(xr + 8 * ldx + 8);
+      mma_m16n8k16_bf16(acc[m], a, b);
+    }
+  }
+  // C fragment: rows g, g + 8; columns n0 + 2t, n0 + 2t + 1
+  const int col = n0 + 2 * t;
+  const float b0 = bias ? bias[col] : 0.f, b1 = bias ? bias[col + 1] : 0.f;
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float v0 = acc[m][2 * h] + b0, v1 = acc[m][2 * h + 1] + b1;
+      if (act == 1) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); }
+      const int64_t row = 16 * m + g + 8 * h;
+      if (c_f32) *reinterpret_cast<float2*>(reinterpret_cast<float*>(c) + row * ldc + col) = make_float2(v0, v1);
+      else *reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(c) + row * ldc + col) = pack_bf16x2(v0, v1);
+    }
   }
 }
 
@@ -330,6 +425,25 @@ extern "C" int dwb_attention_decode(const void* q, int64_t ldq, const void* k_ne
   attn_decode_kernel<<<dim3(H, B), AD_THREADS, smem, (cudaStream_t)stream>>>(
       (const bf16*)q, ldq, (const bf16*)k_new, (const bf16*)v_new, ld_new, (bf16*)k_cache, (bf16*)v_cache, ld_cache, cache_rows, (bf16*)o, ldo,
       fixed_len, pos_dev, scale * 1.4426950408889634f);
+  DWB_LAUNCH_OK();
+  return DWB_OK;
+}
+
+extern "C" int dwb_gemm_skinny_bf16(const void* X, int64_t ldx, const void* W, int64_t ldw, void* C, int64_t ldc, int c_f32, int M, int N, int K,
+                                    const float* bias, int act, void* stream) {
+  DWB_CHECK_ARG(X && W && C, "dwb_gemm_skinny_bf16: null operand");
+  DWB_CHECK_ARG(M > 0 && M <= 64 && (M % 16) == 0 && (N % 8) == 0 && (K % 16) == 0, "dwb_gemm_skinny_bf16: needs M in {16,32,48,64}, N %% 8 == 0, K %% 16 == 0 (M=%d N=%d K=%d)", M, N, K);
+  DWB_CHECK_ARG((ldx % 2) == 0 && (ldw % 2) == 0 && (ldc % 2) == 0 && (reinterpret_cast<uintptr_t>(X) & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 3) == 0 &&
+                    (reinterpret_cast<uintptr_t>(C) & (c_f32 ? 7 : 3)) == 0, "dwb_gemm_skinny_bf16: operands must keep 4 B (8 B fp32 C) alignment per pair");
+  DWB_CHECK_ARG(act == 0 || act == 1, "dwb_gemm_skinny_bf16: unknown activation %d", act);
+  const dim3 grid(N / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (M / 16) {
+    case 1: gemm_skinny_kernel<1><<<grid, 32, 0, st>>>((const bf16*)X, ldx, (const bf16*)W, ldw, bias, C, ldc, c_f32, N, K, act); break;
+    case 2: gemm_skinny_kernel<2><<<grid, 32, 0, st>>>((const bf16*)X, ldx, (const bf16*)W, ldw, bias, C, ldc, c_f32, N, K, act); break;
+    case 3: gemm_skinny_kernel<3><<<grid, 32, 0, st>>>((const bf16*)X, ldx, (const bf16*)W, ldw, bias, C, ldc, c_f32, N, K, act); break;
+    default: gemm_skinny_kernel<4><<<grid, 32, 0, st>>>((const bf16*)X, ldx, (const bf16*)W, ldw, bias, C, ldc, c_f32, N, K, act); break;
+  }
   DWB_LAUNCH_OK();
   return DWB_OK;
 }

@@ -168,21 +168,21 @@ class DecodeSession:
             ws = engine._attn_weights(st, k + ".sa", layer.self_attn, fuse_qkv=True)
             g, b_ = engine._ln(st, k + ".ln1", layer.self_attn_layer_norm)
             x1, h1, _, _ = ops.add_layernorm(x, y, g, b_, rows=B, d=d)
-            qkv = ops.gemm(h1, ws["wqkv"], bias=ws["bqkv"])
+            qkv = ops.gemm_small_m(h1, ws["wqkv"], bias=ws["bqkv"])
             kv = self.self_kv[i]
             o1 = ops.attention_decode(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], kv[:, :d], kv[:, d:], self.t_max, B, H, pos_dev=self.pos)
-            y1 = ops.gemm(o1, ws["wo"], bias=ws["bo"])
+            y1 = ops.gemm_small_m(o1, ws["wo"], bias=ws["bo"])
             wc = engine._attn_weights(st, k + ".ca", layer.encoder_attn, fuse_qkv=False)
             g, b_ = engine._ln(st, k + ".ln2", layer.encoder_attn_layer_norm)
             x2, h2, _, _ = ops.add_layernorm(x1, y1, g, b_, rows=B, d=d)
-            qc = ops.gemm(h2, wc["wq"], bias=wc["bq"])
+            qc = ops.gemm_small_m(h2, wc["wq"], bias=wc["bq"])
             ckv = self.cross_kv[i]
             o2 = ops.attention_decode(qc, None, None, ckv[:, :d], ckv[:, d:], S, B, H, fixed_len=S)
-            y2 = ops.gemm(o2, wc["wo"], bias=wc["bo"])
+            y2 = ops.gemm_small_m(o2, wc["wo"], bias=wc["bo"])
             g, b_ = engine._ln(st, k + ".ln3", layer.final_layer_norm)
             x3, h3, _, _ = ops.add_layernorm(x2, y2, g, b_, rows=B, d=d)
-            a = ops.gemm(h3, engine.bf16_of(c, k + ".fc1.w", layer.fc1.weight), bias=engine.f32_of(c, k + ".fc1.b", layer.fc1.bias), act=1)
-            y3 = ops.gemm(a, engine.bf16_of(c, k + ".fc2.w", layer.fc2.weight), bias=engine.f32_of(c, k + ".fc2.b", layer.fc2.bias))
+            a = ops.gemm_small_m(h3, engine.bf16_of(c, k + ".fc1.w", layer.fc1.weight), bias=engine.f32_of(c, k + ".fc1.b", layer.fc1.bias), act=1)
+            y3 = ops.gemm_small_m(a, engine.bf16_of(c, k + ".fc2.w", layer.fc2.weight), bias=engine.f32_of(c, k + ".fc2.b", layer.fc2.bias))
             x, y = x3, y3
         g, b_ = engine._ln(st, "ln_f", dec.layer_norm)
         _, hf, _, _ = ops.add_layernorm(x, y, g, b_, rows=B, d=d, write_x=False)

@@ -181,6 +181,21 @@ def embed_bwd(ids, dx, dE, dP, B, T, d, vocab, padding_idx):
     _abi.call("dwb_embed_bwd", _ptr(ids), _ptr(dx), _ptr(dE), _ptr(dP), B, T, d, vocab, int(padding_idx), _stream())
 
 
+def gemm_small_m(a, b, *, bias=None, act=0, out_dtype=BF16):
+    """out[M,N] = act(A . B^T + bias) for the decode step (M = batch rows).  Batch sizes of 16 / 32 / 48 / 64 take the weight-streaming
+    skinny kernel (dwb_gemm_skinny_bf16); anything else goes through the tcgen05 GEMM."""
+    M, K = a.shape
+    N = b.shape[0]
+    if not (M in (16, 32, 48, 64) and N % 8 == 0 and K % 16 == 0 and a.stride(0) % 2 == 0 and b.stride(0) % 2 == 0):
+        return gemm(a, b, bias=bias, act=act, out_dtype=out_dtype)
+    _check2d(a, BF16, "gemm_small_m A")
+    _check2d(b, BF16, "gemm_small_m B")
+    out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    _abi.call("dwb_gemm_skinny_bf16", _ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(out), out.stride(0), int(out_dtype == F32), M, N, K,
+              _ptr(bias), int(act), _stream())
+    return out
+
+
 def embed_decode(seq, pos_dev, E, P, d, vocab):
     """x[b] = E[seq[b, pos]] + P[pos] (pos read on the device) -> fp32 [B, d]."""
     assert seq.dtype == torch.int64 and seq.dim() == 2 and seq.stride(1) == 1 and pos_dev.dtype == torch.int32 and E.dtype == P.dtype

@@ -421,3 +421,22 @@ def test_greedy_pick_with_timestamp_rules_matches_hf_processor_semantics():
             ops.greedy_pick_timestamps(buf, V, bias_all, bias_begin, begin, seq, begin, finished, eos, 99, pos, ts_begin, max_init)
             assert torch.equal(seq[:, t].cpu(), want), (max_init, ids[0].tolist(), seq[:, t].cpu(), want)
             assert torch.equal(finished.cpu().bool(), want == eos)
+
+
+@pytest.mark.parametrize("M,N,K,act,f32", [(32, 1280, 1280, 0, False), (16, 3840, 1280, 0, False), (64, 5120, 1280, 1, False), (48, 1280, 5120, 0, False),
+                                          (32, 264, 80, 1, True), (3, 1280, 1280, 0, False)])
+def test_skinny_decode_gemm_against_torch(M, N, K, act, f32):
+    """dwb_gemm_skinny_bf16 (decode-step projections, M = batch rows) vs torch fp32 on the same bf16 operands; M = 3 takes the
+    tcgen05 fallback inside ops.gemm_small_m."""
+    from distil_whisper_b200 import ops
+    torch.manual_seed(M + N)
+    x = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda") * 0.1
+    out = ops.gemm_small_m(x, w, bias=b, act=act, out_dtype=torch.float32 if f32 else torch.bfloat16)
+    ref = x.float() @ w.float().t() + b
+    if act:
+        ref = F.gelu(ref)
+    assert out.shape == (M, N)
+    tol = 2e-3 if f32 else 1e-2
+    assert (out.float() - ref).abs().max() < tol * max(1.0, float(ref.abs().max())), float((out.float() - ref).abs().max())
