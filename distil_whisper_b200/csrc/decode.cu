@@ -162,70 +162,77 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(const bf16* __r
 // ------------------------------------------------------------------------------------------------
 // Skinny GEMM for the decode step: C[M, N] = act(X[M, K] . W[N, K]^T + bias) with M = the batch (16 .. 64 rows).  The projection is
 // weight-bandwidth bound (every weight is used by M rows only): the persistent 128-row tcgen05 tiles give such a problem 10 - 40 CTAs
-// and 11 - 14 us; here every warp owns 8 output columns (N / 8 warps = 160 - 640 CTAs of one warp), streams its 8 weight rows once from
-// HBM with four k-steps of loads in flight, takes the activations through L1 (all warps read the same X), and multiplies with
-// mma.sync.m16n8k16 (bf16, fp32 accumulate).  Whisper decoder projections at batch 32: ~3 us.
+// and 11 - 14 us; here N / 8 CTAs (160 - 640) of four warps stream the weights once from HBM, take the activations through L1 (all
+// CTAs read the same X), and multiply with mma.sync.m16n8k16 (bf16, fp32 accumulate).
 __device__ __forceinline__ void mma_m16n8k16_bf16(float* c, const uint32_t* a, const uint32_t* b) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+// Layout trick: the reduction index may be visited in any order as long as A and B agree, so lane (g, t) takes the 16 consecutive
+// k of its row that start at 16 t inside each 64-wide chunk (two 16 B loads) and feeds them to four k-steps; every load is a full
+// 32 B sector and a warp has all the weights of its k-range in flight at once.  A CTA = 8 output columns x 4 k-ranges (4 warps),
+// partial sums combined through shared memory.
 template <int MT>      // 16-row tiles of X: M = 16 * MT
-__global__ void __launch_bounds__(32) gemm_skinny_kernel(const bf16* __restrict__ x, int64_t ldx, const bf16* __restrict__ w, int64_t ldw,
-                                                        const float* __restrict__ bias, void* __restrict__ c, int64_t ldc, int c_f32,
-                                                        int N, int K, int act) {
-  const int lane = threadIdx.x, g = lane >> 2, t = lane & 3;
+__global__ void __launch_bounds__(128) gemm_skinny_kernel(const bf16* __restrict__ x, int64_t ldx, const bf16* __restrict__ w, int64_t ldw,
+                                                         const float* __restrict__ bias, void* __restrict__ c, int64_t ldc, int c_f32,
+                                                         int N, int K, int act) {
+  __shared__ float s_part[3][MT][4][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int n0 = blockIdx.x * 8;
-  if (n0 >= N) return;
   float acc[MT][4];
 #pragma unroll
   for (int m = 0; m < MT; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f; }
-  const bf16* wrow = w + (int64_t)(n0 + g) * ldw + 2 * t;            // B fragment: column n0 + g, k = k0 + 2t (+1), k0 + 8 + 2t (+1)
-  const bf16* xrow = x + (int64_t)g * ldx + 2 * t;                   // A fragment rows g, g + 8 of each 16-row tile
-  constexpr int UNR = 4;
-  int k0 = 0;
-  for (; k0 + 16 * UNR <= K; k0 += 16 * UNR) {
-    uint32_t b[UNR][2], a[UNR][MT][4];
+  const int kq = K >> 2;                                             // this warp's k-range: [warp * kq, (warp + 1) * kq), kq % 64 == 0
+  const bf16* wrow = w + (int64_t)(n0 + g) * ldw + warp * kq + 16 * t;
+  const bf16* xrow = x + (int64_t)g * ldx + warp * kq + 16 * t;
+  constexpr int UNR = 5;                                             // chunks of 64 k with their weight loads in flight together
+  for (int kc = 0; kc < kq; kc += 64 * UNR) {
+    uint4 b[UNR][2];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-      const int kk = k0 + 16 * u;
-      b[u][0] = *reinterpret_cast<const uint32_t*>(wrow + kk);
-      b[u][1] = *reinterpret_cast<const uint32_t*>(wrow + kk + 8);
-#pragma unroll
-      for (int m = 0; m < MT; ++m) {
-        const bf16* xr = xrow + (int64_t)(16 * m) * ldx + kk;
-        a[u][m][0] = *reinterpret_cast<const uint32_t*>(xr);
-        a[u][m][1] = *reinterpret_cast<const uint32_t*>(xr + 8 * ldx);
-        a[u][m][2] = *reinterpret_cast<const uint32_t*>(xr + 8);
-        a[u][m][3] = *reinterpret_cast<const uint32_t*>(xr + 8 * ldx + 8);
+      if (kc + 64 * u < kq) {
+        b[u][0] = *reinterpret_cast<const uint4*>(wrow + kc + 64 * u);
+        b[u][1] = *reinterpret_cast<const uint4*>(wrow + kc + 64 * u + 8);
       }
     }
 #pragma unroll
-    for (int u = 0; u < UNR; ++u)
+    for (int u = 0; u < UNR; ++u) {
+      if (kc + 64 * u < kq) {
+        const uint32_t bw[8] = {b[u][0].x, b[u][0].y, b[u][0].z, b[u][0].w, b[u][1].x, b[u][1].y, b[u][1].z, b[u][1].w};
 #pragma unroll
-      for (int m = 0; m < MT; ++m) mma_m16n8k16_bf16(acc[m], a[u][m], b[u]);
-  }
-  for (; k0 < K; k0 += 16) {
-    uint32_t b[2];
-    b[0] = *reinterpret_cast<const uint32_t*>(wrow + k0);
-    b[1] = *reinterpret_cast<const uint32_t*>(wrow + k0 + 8);
+        for (int m = 0; m < MT; ++m) {
+          const bf16* xr = xrow + (int64_t)(16 * m) * ldx + kc + 64 * u;
+          const uint4 a00 = *reinterpret_cast<const uint4*>(xr), a01 = *reinterpret_cast<const uint4*>(xr + 8);
+          const uint4 a10 = *reinterpret_cast<const uint4*>(xr + 8 * ldx), a11 = *reinterpret_cast<const uint4*>(xr + 8 * ldx + 8);
+          const uint32_t r0[8] = {a00.x, a00.y, a00.z, a00.w, a01.x, a01.y, a01.z, a01.w};      // row g:     this lane's 16 k
+          const uint32_t r1[8] = {a10.x, a10.y, a10.z, a10.w, a11.x, a11.y, a11.z, a11.w};      // row g + 8
 #pragma unroll
-    for (int m = 0; m < MT; ++m) {
-      const bf16* xr = xrow + (int64_t)(16 * m) * ldx + k0;
-      uint32_t a[4];
-      a[0] = *reinterpret_cast<const uint32_t*>(xr);
-      a[1] = *reinterpret_cast<const uint32_t*>(xr + 8 * ldx);
-      a[2] = *reinterpret_cast<const uint32_t*>(xr + 8);
-      a[3] = *reinterpret_cast<const uint32_t*>(xr + 8 * ldx + 8);
-      mma_m16n8k16_bf16(acc[m], a, b);
+          for (int st = 0; st < 4; ++st) {                       // k-step st uses the lane's elements 4 st .. 4 st + 3
+            const uint32_t af[4] = {r0[2 * st], r1[2 * st], r0[2 * st + 1], r1[2 * st + 1]};
+            const uint32_t bf[2] = {bw[2 * st], bw[2 * st + 1]};
+            mma_m16n8k16_bf16(acc[m], af, bf);
+          }
+        }
+      }
     }
   }
+  if (warp > 0) {
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s_part[warp - 1][m][i][lane] = acc[m][i];
+  }
+  __syncthreads();
+  if (warp > 0) return;
   // C fragment: rows g, g + 8; columns n0 + 2t, n0 + 2t + 1
   const int col = n0 + 2 * t;
   const float b0 = bias ? bias[col] : 0.f, b1 = bias ? bias[col + 1] : 0.f;
 #pragma unroll
   for (int m = 0; m < MT; ++m) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[m][i] += (s_part[0][m][i][lane] + s_part[1][m][i][lane]) + s_part[2][m][i][lane];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       float v0 = acc[m][2 * h] + b0, v1 = acc[m][2 * h + 1] + b1;
@@ -432,17 +439,17 @@ extern "C" int dwb_attention_decode(const void* q, int64_t ldq, const void* k_ne
 extern "C" int dwb_gemm_skinny_bf16(const void* X, int64_t ldx, const void* W, int64_t ldw, void* C, int64_t ldc, int c_f32, int M, int N, int K,
                                     const float* bias, int act, void* stream) {
   DWB_CHECK_ARG(X && W && C, "dwb_gemm_skinny_bf16: null operand");
-  DWB_CHECK_ARG(M > 0 && M <= 64 && (M % 16) == 0 && (N % 8) == 0 && (K % 16) == 0, "dwb_gemm_skinny_bf16: needs M in {16,32,48,64}, N %% 8 == 0, K %% 16 == 0 (M=%d N=%d K=%d)", M, N, K);
-  DWB_CHECK_ARG((ldx % 2) == 0 && (ldw % 2) == 0 && (ldc % 2) == 0 && (reinterpret_cast<uintptr_t>(X) & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 3) == 0 &&
-                    (reinterpret_cast<uintptr_t>(C) & (c_f32 ? 7 : 3)) == 0, "dwb_gemm_skinny_bf16: operands must keep 4 B (8 B fp32 C) alignment per pair");
+  DWB_CHECK_ARG(M > 0 && M <= 64 && (M % 16) == 0 && (N % 8) == 0 && (K % 256) == 0, "dwb_gemm_skinny_bf16: needs M in {16,32,48,64}, N %% 8 == 0, K %% 256 == 0 (M=%d N=%d K=%d)", M, N, K);
+  DWB_CHECK_ARG((ldx % 8) == 0 && (ldw % 8) == 0 && (ldc % 2) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(C) & (c_f32 ? 7 : 3)) == 0, "dwb_gemm_skinny_bf16: X / W need 16 B aligned rows, C 4 B (8 B fp32) pairs");
   DWB_CHECK_ARG(act == 0 || act == 1, "dwb_gemm_skinny_bf16: unknown activation %d", act);
   const dim3 grid(N / 8);
   cudaStream_t st = (cudaStream_t)stream;
   switch (M / 16) {
-    case 1: gemm_skinny_kernel<1><<<grid, 32, 0, st>>>((const bf16*)X, ldx, (const bf16*)W, ldw, bias, C, ldc, c_f32, N, K, act); break;
-    case 2: gemm_skinny_kernel<2><<<grid, 32, 0, st>>>((const bf16*)X, ldx, (const bf16*)W, ldw, bias, C, ldc, c_f32, N, K, act); break;
-    case 3: gemm_skinny_kernel<3><<<grid, 32, 0, st>>>((const bf16*)X, ldx, (const bf16*)W, ldw, bias, C, ldc, c_f32, N, K, act); break;
-    default: gemm_skinny_kernel<4><<<grid, 32, 0, st>>>((const bf16*)X, ldx, (const bf16*)W, ldw, bias, C, ldc, c_f32, N, K, act); break;
+    case 1: gemm_skinny_kernel<1><<<grid, 128, 0, st>>>((const bf16*)X, ldx, (const bf16*)W, ldw, bias, C, ldc, c_f32, N, K, act); break;
+    case 2: gemm_skinny_kernel<2><<<grid, 128, 0, st>>>((const bf16*)X, ldx, (const bf16*)W, ldw, bias, C, ldc, c_f32, N, K, act); break;
+    case 3: gemm_skinny_kernel<3><<<grid, 128, 0, st>>>((const bf16*)X, ldx, (const bf16*)W, ldw, bias, C, ldc, c_f32, N, K, act); break;
+    default: gemm_skinny_kernel<4><<<grid, 128, 0, st>>>((const bf16*)X, ldx, (const bf16*)W, ldw, bias, C, ldc, c_f32, N, K, act); break;
   }
   DWB_LAUNCH_OK();
   return DWB_OK;

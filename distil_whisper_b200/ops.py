@@ -186,7 +186,8 @@ def gemm_small_m(a, b, *, bias=None, act=0, out_dtype=BF16):
     skinny kernel (dwb_gemm_skinny_bf16); anything else goes through the tcgen05 GEMM."""
     M, K = a.shape
     N = b.shape[0]
-    if not (M in (16, 32, 48, 64) and N % 8 == 0 and K % 16 == 0 and a.stride(0) % 2 == 0 and b.stride(0) % 2 == 0):
+    if not (M in (16, 32, 48, 64) and N % 8 == 0 and K % 256 == 0 and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0
+            and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0):
         return gemm(a, b, bias=bias, act=act, out_dtype=out_dtype)
     _check2d(a, BF16, "gemm_small_m A")
     _check2d(b, BF16, "gemm_small_m B")

@@ -119,7 +119,8 @@ int dwb_embed_bwd(const int64_t* ids, const float* dx, float* dE, float* dP, int
  *                        positions are kept, finished rows get `pad`, `finished` is updated on `eos` (HF:generation/utils.py _sample).
  * dwb_decode_advance:    pos += 1; done_at = sequence length at which every row had finished (0 until then). */
 /* dwb_gemm_skinny_bf16: C[M,N] = act(X[M,K] . W[N,K]^T + bias) for the decode step's batch-sized M (16, 32, 48 or 64 rows; N % 8 == 0,
- * K % 16 == 0): weight-bandwidth bound, one warp per 8 output columns, mma.sync.m16n8k16 (same nn.Linear semantics as dwb_gemm_bf16). */
+ * K % 256 == 0, 16 B aligned rows): weight-bandwidth bound, N / 8 CTAs of four warps (8 columns x 4 k-ranges), mma.sync.m16n8k16 (same
+ * nn.Linear semantics as dwb_gemm_bf16). */
 int dwb_gemm_skinny_bf16(const void* X, int64_t ldx, const void* W, int64_t ldw, void* C, int64_t ldc, int c_f32, int M, int N, int K,
                          const float* bias, int act, void* stream);
 int dwb_embed_decode(const int64_t* seq, int seq_ld, const int* pos_dev, const void* E, const void* P, int table_is_f32, float* x, int B,
