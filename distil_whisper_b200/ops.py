@@ -181,12 +181,16 @@ def embed_bwd(ids, dx, dE, dP, B, T, d, vocab, padding_idx):
     _abi.call("dwb_embed_bwd", _ptr(ids), _ptr(dx), _ptr(dE), _ptr(dP), B, T, d, vocab, int(padding_idx), _stream())
 
 
+import os as _os
+_SKINNY = _os.environ.get("DWB_SKINNY_GEMM", "1") != "0"      # A/B switch for the decode-step projections
+
+
 def gemm_small_m(a, b, *, bias=None, act=0, out_dtype=BF16):
     """out[M,N] = act(A . B^T + bias) for the decode step (M = batch rows).  Batch sizes of 16 / 32 / 48 / 64 take the weight-streaming
     skinny kernel (dwb_gemm_skinny_bf16); anything else goes through the tcgen05 GEMM."""
     M, K = a.shape
     N = b.shape[0]
-    if not (M in (16, 32, 48, 64) and N % 8 == 0 and K % 256 == 0 and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0
+    if not (_SKINNY and M in (16, 32, 48, 64) and N % 8 == 0 and K % 256 == 0 and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0
             and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0):
         return gemm(a, b, bias=bias, act=act, out_dtype=out_dtype)
     _check2d(a, BF16, "gemm_small_m A")

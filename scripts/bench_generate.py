@@ -12,8 +12,11 @@ import bench  # noqa: E402
 from distil_whisper_b200.modeling import DistilWhisperB200ForConditionalGeneration  # noqa: E402
 
 res = []
-for name, dims, B in (("large-v3 teacher (bf16)", bench.TEACHER, 32), ("large-v3 teacher (bf16)", bench.TEACHER, 64),
-                      ("distil-large-v3 student (fp32 masters)", bench.STUDENT, 32)):
+CASES = (("large-v3 teacher (bf16)", bench.TEACHER, 32), ("large-v3 teacher (bf16)", bench.TEACHER, 64),
+         ("distil-large-v3 student (fp32 masters)", bench.STUDENT, 32))
+if len(sys.argv) > 1:
+    CASES = tuple(c for c in CASES if str(c[2]) in sys.argv[1:] and "teacher" in c[0])
+for name, dims, B in CASES:
     torch.manual_seed(0)
     with torch.device("cuda"):
         m = DistilWhisperB200ForConditionalGeneration(dims)
