@@ -23,6 +23,7 @@ SIGNATURES = {
     "dwb_abi_version": (_i, []),
     "dwb_check_device": (_i, []),
     "dwb_launch_count": (_l, [_i]),
+    "dwb_set_row_walk": (_i, [_i]),
     "dwb_scale_bf16_dev": (_i, [_p, _l, _p, _p]),
     "dwb_gemm_bf16": (_i, [_p, _l, _i, _p, _l, _i, _p, _l, _i, _i, _i, _i, _p, _i, _f, _i, _i, _p]),
     "dwb_attention_fwd": (_i, [_p, _l, _p, _l, _p, _l, _p, _l, _p, _i, _i, _i, _i, _i, _i, _f, _p]),

@@ -37,3 +37,14 @@ extern "C" int dwb_check_device(void) {
   }
   return DWB_OK;
 }
+
+// Direction in which the next GEMM / LayerNorm / attention-forward launches walk the rows of their [rows, features] operands:
+// 0 = first to last (default), 1 = last to first.  A chain of kernels that stream a tensor larger than the 126 MB L2 alternates the
+// direction, so that every consumer starts on the rows its producer wrote last (still in L2) instead of on the ones already evicted
+// (engine.encoder_forward).  Host-side launch parameter; not thread-safe across concurrently launching host threads.
+static int g_row_walk_reverse = 0;
+extern "C" int dwb_row_walk_reverse(void) { return g_row_walk_reverse; }
+extern "C" int dwb_set_row_walk(int reverse) {
+  g_row_walk_reverse = reverse ? 1 : 0;
+  return DWB_OK;
+}

@@ -56,6 +56,7 @@ __device__ __forceinline__ float2 poly_exp2_pair(float2 x) {
 
 struct TcAttnParams {
   int H, Sq, Sk, causal;
+  int reverse;          // CTAs take (batch, head, query tile) from the last to the first (dwb_set_row_walk)
   float scale_log2;     // scale * log2(e)
   float scale;
   float* lse;           // [B, H, Sq] or null
@@ -91,8 +92,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * TA_BQ;
-  const int b = blockIdx.y / p.H, h = blockIdx.y % p.H;
+  const int bx = p.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x, by = p.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const int q0 = bx * TA_BQ;
+  const int b = by / p.H, h = by % p.H;
   // causal: keys beyond the last query of this tile are never attended to
   const int n_kv = ceil_div(p.causal ? min(p.Sk, q0 + TA_BQ) : p.Sk, TA_BK);
 
@@ -495,6 +497,7 @@ extern "C" int dwb_attention_fwd_tc(const void* q, int64_t ldq, const void* k, i
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse;
+  p.reverse = dwb_row_walk_reverse();
   dim3 grid(ceil_div(Sq, TA_BQ), B * H);
   // (Two variants with two softmax threads per query row -- 16 softmax warps per SM -- were built and measured in round 1:
   //  with a per-tile pair barrier 0.70 ms, with each thread reducing the full-row maximum itself (no exchange) 0.62 ms,

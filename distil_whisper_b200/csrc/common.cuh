@@ -13,6 +13,9 @@
 #define DWB_ERR_UNSUPPORTED -3
 
 extern "C" void dwb_set_error(const char* fmt, ...);
+// Row-walk direction of the next launches of the streaming kernels (GEMM tile walk, LayerNorm rows, attention batches): host-side
+// launch parameter set through dwb_set_row_walk (abi.cu).
+extern "C" int dwb_row_walk_reverse(void);
 
 #define DWB_CHECK_ARG(cond, ...)                 \
   do {                                           \

@@ -16,11 +16,14 @@ __global__ void __launch_bounds__(256, MINB) add_layernorm_kernel(const float* _
                                                             const bf16* __restrict__ y, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float* __restrict__ x_out,
                                                             bf16* __restrict__ ln_out, float* __restrict__ mean_out,
-                                                            float* __restrict__ rstd_out, int rows, int d, float eps) {
+                                                            float* __restrict__ rstd_out, int rows, int d, float eps, int reverse) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
-  const int row = warp;
+  // Rows are visited from the last to the first: the GEMM that produced x (TMA reduce-add epilogue) walks its tiles with m ascending,
+  // so the END of x is what is still in the 126 MB L2 when this kernel starts, and the GEMM that consumes the normalised rows starts at
+  // row 0 -- the rows this kernel writes last.
+  const int row = reverse ? rows - 1 - warp : warp;
   const int src_row = x_rows_mod > 0 ? row % x_rows_mod : row;
   const float4* xr = reinterpret_cast<const float4*>(x_in + (int64_t)src_row * d);
   const uint2* yr = y ? reinterpret_cast<const uint2*>(y + (int64_t)row * d) : nullptr;
@@ -396,8 +399,9 @@ extern "C" int dwb_add_layernorm(const float* x_in, int x_rows_mod, const void* 
   cudaStream_t st = (cudaStream_t)stream;
 #define DWB_LN_LAUNCH(NV, MINB)                                                                                              \
   add_layernorm_kernel<NV, MINB><<<grid, 256, 0, st>>>(x_in, x_rows_mod, (const bf16*)y_bf16, gamma, beta, x_out, (bf16*)ln_out_bf16, \
-                                                       mean_out, rstd_out, rows, d, eps)
+                                                       mean_out, rstd_out, rows, d, eps, reverse)
   static const int wide_only = [] { const char* e = getenv("DWB_LN_WIDE"); return e ? atoi(e) : 0; }();   // A/B switch for the microbench
+  const int reverse = dwb_row_walk_reverse();
   if (wide_only) DWB_LN_LAUNCH(16, 2);
   else if (nvec <= 3) DWB_LN_LAUNCH(3, 4);
   else if (nvec <= 4) DWB_LN_LAUNCH(4, 4);

@@ -41,6 +41,7 @@ struct GemmParams {
   int act;              // 0 none, 1 gelu(erf)
   float alpha;
   const float* bias;    // [N] or null
+  int reverse;          // walk the tiles from the last row block to the first (see dwb_set_row_walk)
 };
 
 template <int BN, int A_MN, int B_MN>
@@ -107,7 +108,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int tile = item % num_tiles;
+        const int tile = p.reverse ? num_tiles - 1 - item % num_tiles : item % num_tiles;
         const int split = item / num_tiles;
         const int m0 = (tile / n_tiles) * BM;
         const int n0 = (tile % n_tiles) * BN;
@@ -199,7 +200,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     int local_it = 0;
     int panel_it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local_it) {
-      const int tile = item % num_tiles;
+      const int tile = p.reverse ? num_tiles - 1 - item % num_tiles : item % num_tiles;
       const int m0 = (tile / n_tiles) * BM + q * 32;
       const int n0 = (tile % n_tiles) * BN;
       const int acc = local_it & 1;
@@ -359,7 +360,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     int stage = 0;
     uint32_t phase = 0;
     for (int item = cluster_id; item < num_items; item += num_clusters) {
-      const int tile = item % num_tiles;
+      const int tile = p.reverse ? num_tiles - 1 - item % num_tiles : item % num_tiles;
       const int split = item / num_tiles;
       const int m0 = (tile / n_tiles) * (2 * BM) + (int)rank * BM;
       const int n0 = (tile % n_tiles) * BN + (int)rank * BNH;     // this CTA's half of the B tile
@@ -446,7 +447,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     int local_it = 0;
     int panel_it = 0;
     for (int item = cluster_id; item < num_items; item += num_clusters, ++local_it) {
-      const int tile = item % num_tiles;
+      const int tile = p.reverse ? num_tiles - 1 - item % num_tiles : item % num_tiles;
       const int m0 = (tile / n_tiles) * (2 * BM) + (int)rank * BM + q * 32;
       const int n0 = (tile % n_tiles) * BN;
       const int acc = local_it & 1;
@@ -722,6 +723,7 @@ extern "C" int dwb_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const v
   p.act = act;
   p.alpha = alpha;
   p.bias = bias;
+  p.reverse = dwb_row_walk_reverse();
   if (split_k > 1 && !accumulate) {
     DWB_CUDA_OK(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));
   }

@@ -189,6 +189,28 @@ def _ln(st, key, ln):
 USE_TC_ATTENTION = True     # tcgen05 encoder attention (attention_tcgen05.cu); False -> mma.sync kernel
 
 
+class _RowWalk:
+    """Alternates the row-walk direction of consecutive streaming kernels (dwb_set_row_walk): every tensor of the 32-utterance encoder
+    pass (123 - 491 MB) is larger than L2, so a consumer that starts where its producer finished finds ~100 MB of its input still in
+    L2 instead of none.  DWB_ROW_WALK=0 keeps every kernel ascending (A/B)."""
+
+    def __init__(self, first_reverse=True):
+        import os
+        self.on = os.environ.get("DWB_ROW_WALK", "1") != "0"
+        self.rev = first_reverse
+
+    def step(self):
+        if self.on:
+            from . import _abi
+            _abi.call("dwb_set_row_walk", int(self.rev))
+            self.rev = not self.rev
+
+    def reset(self):
+        if self.on:
+            from . import _abi
+            _abi.call("dwb_set_row_walk", 0)
+
+
 def _conv1_w(st, ld):
     enc = st.m
     d, C = enc.conv1.weight.shape[0], enc.conv1.weight.shape[1]
@@ -241,31 +263,43 @@ def encoder_forward(st: _State, input_features, save=False):
     # sub-layer output is never rounded to bf16 before the residual add.
     pos = f32_of(c, "pos", enc.embed_positions.weight)[:S]
     x = torch.empty((M, d), dtype=F32, device=mel.device)
-    for i, layer in enumerate(enc.layers):
-        k = f"l{i}"
-        w = _attn_weights(st, k + ".sa", layer.self_attn, fuse_qkv=True)
-        g, b_ = _ln(st, k + ".ln1", layer.self_attn_layer_norm)
-        if i == 0:
-            _, h, _, _ = ops.add_layernorm(pos, y, g, b_, rows=M, d=d, x_rows_mod=S, x_out=x)
-            del y
-        else:
+    walk = _RowWalk(first_reverse=True)         # the conv2 GEMM above finished on the last rows of y
+    try:
+        for i, layer in enumerate(enc.layers):
+            k = f"l{i}"
+            w = _attn_weights(st, k + ".sa", layer.self_attn, fuse_qkv=True)
+            g, b_ = _ln(st, k + ".ln1", layer.self_attn_layer_norm)
+            walk.step()
+            if i == 0:
+                _, h, _, _ = ops.add_layernorm(pos, y, g, b_, rows=M, d=d, x_rows_mod=S, x_out=x)
+                del y
+            else:
+                _, h, _, _ = ops.add_layernorm(x, None, g, b_, rows=M, d=d, write_x=False)
+            walk.step()
+            qkv = ops.gemm(h, w["wqkv"], bias=w["bqkv"])
+            walk.step()
+            o, _ = ops.attention_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], B, H, S, S, causal=False, out=h,
+                                     need_lse=False, use_tc=USE_TC_ATTENTION)
+            del qkv
+            walk.step()
+            ops.gemm(o, w["wo"], bias=w["bo"], out=x, accumulate=True)                       # x += out_proj(attn)
+            g, b_ = _ln(st, k + ".ln2", layer.final_layer_norm)
+            walk.step()
             _, h, _, _ = ops.add_layernorm(x, None, g, b_, rows=M, d=d, write_x=False)
-        qkv = ops.gemm(h, w["wqkv"], bias=w["bqkv"])
-        o, _ = ops.attention_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], B, H, S, S, causal=False, out=h,
-                                 need_lse=False, use_tc=USE_TC_ATTENTION)
-        del qkv
-        ops.gemm(o, w["wo"], bias=w["bo"], out=x, accumulate=True)                       # x += out_proj(attn)
-        g, b_ = _ln(st, k + ".ln2", layer.final_layer_norm)
-        _, h, _, _ = ops.add_layernorm(x, None, g, b_, rows=M, d=d, write_x=False)
-        a = ops.gemm(h, bf16_of(c, k + ".fc1.w", layer.fc1.weight), bias=f32_of(c, k + ".fc1.b", layer.fc1.bias), act=1)
-        ops.gemm(a, bf16_of(c, k + ".fc2.w", layer.fc2.weight), bias=f32_of(c, k + ".fc2.b", layer.fc2.bias), out=x,
-                 accumulate=True)                                                          # x += fc2(gelu(fc1))
-        del a
-    g, b_ = _ln(st, "ln_f", enc.layer_norm)
-    if len(enc.layers) == 0:
-        _, out, _, _ = ops.add_layernorm(pos, y, g, b_, rows=M, d=d, x_rows_mod=S, write_x=False)
-    else:
-        _, out, _, _ = ops.add_layernorm(x, None, g, b_, rows=M, d=d, write_x=False)
+            walk.step()
+            a = ops.gemm(h, bf16_of(c, k + ".fc1.w", layer.fc1.weight), bias=f32_of(c, k + ".fc1.b", layer.fc1.bias), act=1)
+            walk.step()
+            ops.gemm(a, bf16_of(c, k + ".fc2.w", layer.fc2.weight), bias=f32_of(c, k + ".fc2.b", layer.fc2.bias), out=x,
+                     accumulate=True)                                                          # x += fc2(gelu(fc1))
+            del a
+        g, b_ = _ln(st, "ln_f", enc.layer_norm)
+        walk.step()
+        if len(enc.layers) == 0:
+            _, out, _, _ = ops.add_layernorm(pos, y, g, b_, rows=M, d=d, x_rows_mod=S, write_x=False)
+        else:
+            _, out, _, _ = ops.add_layernorm(x, None, g, b_, rows=M, d=d, write_x=False)
+    finally:
+        walk.reset()
     return out, None
 
 

@@ -36,6 +36,10 @@ const char* dwb_last_error(void);
 int dwb_abi_version(void);
 /* Kernel launches issued by the library since the last reset (host-side count; bench.py's `gpu_launches`). */
 int64_t dwb_launch_count(int reset);
+/* Direction in which the NEXT dwb_gemm_bf16 / dwb_add_layernorm / dwb_attention_fwd_tc launches walk the rows of their operands
+ * (0 = first to last, the default; 1 = last to first).  Alternating it along a chain of kernels that stream tensors larger than L2 makes
+ * every consumer start on the rows its producer wrote last.  Results are unaffected. */
+int dwb_set_row_walk(int reverse);
 /* 0 iff the current CUDA device is compute capability 10.x (B200).  There is no CPU fallback. */
 int dwb_check_device(void);
 

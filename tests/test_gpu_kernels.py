@@ -440,3 +440,36 @@ def test_skinny_decode_gemm_against_torch(M, N, K, act, f32):
     assert out.shape == (M, N)
     tol = 2e-3 if f32 else 1e-2
     assert (out.float() - ref).abs().max() < tol * max(1.0, float(ref.abs().max())), float((out.float() - ref).abs().max())
+
+
+def test_reversed_row_walk_gives_identical_results():
+    """dwb_set_row_walk(1): GEMM tile walk (single-CTA and CTA-pair kernels), LayerNorm rows and attention batches run from the last row
+    block to the first (L2 reuse along the encoder's kernel chain) -- the results must be bit-identical to the ascending walk."""
+    from distil_whisper_b200 import _abi, ops
+    torch.manual_seed(3)
+    a = (torch.randn(3000, 1280, device="cuda") * 0.3).bfloat16()
+    w = (torch.randn(3840, 1280, device="cuda") * 0.03).bfloat16()
+    bias = torch.randn(3840, device="cuda") * 0.1
+    x = torch.randn(3000, 1280, device="cuda")
+    g, b_ = torch.randn(1280, device="cuda"), torch.randn(1280, device="cuda")
+    B, H, S = 2, 20, 1500
+    qkv = (torch.randn(B * S, 3 * H * 64, device="cuda") * 0.5).bfloat16()
+    acc0 = torch.randn(3000, 3840, device="cuda")
+
+    def run():
+        outs = [ops.gemm(a, w, bias=bias, act=1), ops.gemm(a, w, bias=bias, impl=2), ops.gemm(a, w, bias=bias, impl=3)]
+        acc = acc0.clone()
+        ops.gemm(a, w, bias=bias, out=acc, accumulate=True)
+        outs.append(acc)
+        outs.append(ops.add_layernorm(x, None, g, b_, rows=3000, d=1280, write_x=False)[1])
+        o, lse = ops.attention_fwd(qkv[:, :1280], qkv[:, 1280:2560], qkv[:, 2560:], B, H, S, S, False, use_tc=True)
+        outs += [o, lse]
+        return outs
+    ref = run()
+    _abi.call("dwb_set_row_walk", 1)
+    try:
+        rev = run()
+    finally:
+        _abi.call("dwb_set_row_walk", 0)
+    for i, (r, v) in enumerate(zip(ref, rev)):
+        assert torch.equal(r, v), i
