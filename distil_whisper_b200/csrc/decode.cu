@@ -31,10 +31,10 @@ __global__ void embed_decode_kernel(const int64_t* __restrict__ seq, int seq_ld,
 // One query row per (head, batch): o = softmax(scale * q K^T) V over cache rows [0, len).
 //   self-attention (k_new != null): the step's own k / v row is first appended to the cache at row pos, len = pos + 1
 //   cross-attention (k_new == null): len = fixed_len (the encoder positions), the cache is read-only
-// Phase 1: thread t scores keys t, t+128, ... (a K row of one head is 128 B: eight 16 B loads, q in registers)
+// Phase 1: thread t scores keys t, t+256, ... (a K row of one head is 128 B: eight 16 B loads, q in registers)
 // Phase 2: block max / sum of exp2
-// Phase 3: warp w accumulates keys w, w+4, ... ; lane l owns output dims 2l, 2l+1 (a V row of one head = one 128 B request)
-constexpr int AD_THREADS = 128;
+// Phase 3: warp w accumulates keys w, w+8, ... ; lane l owns output dims 2l, 2l+1 (a V row of one head = one 128 B request)
+constexpr int AD_THREADS = 256;      // 8 warps: the V pass is a chain of dependent load rounds per warp, more warps = fewer rounds
 
 __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restrict__ k_new,
                                                                  const bf16* __restrict__ v_new, int64_t ld_new, bf16* __restrict__ k_cache,
@@ -96,7 +96,9 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(const bf16* __r
   mx = warp_max(mx);
   if (lane == 0) s_red[warp] = mx;
   __syncthreads();
-  mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+  mx = s_red[0];
+#pragma unroll
+  for (int w = 1; w < AD_THREADS / 32; ++w) mx = fmaxf(mx, s_red[w]);
   __syncthreads();
   float sum = 0.f;
   for (int k = tid; k < len; k += AD_THREADS) {
@@ -107,7 +109,10 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(const bf16* __r
   sum = warp_sum(sum);
   if (lane == 0) s_red[warp] = sum;
   __syncthreads();
-  const float inv = 1.f / (s_red[0] + s_red[1] + s_red[2] + s_red[3]);
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < AD_THREADS / 32; ++w) tot += s_red[w];
+  const float inv = 1.f / tot;
   float a0 = 0.f, a1 = 0.f;
   int k = warp;
   constexpr int NW = AD_THREADS / 32, UNR = 16;
@@ -153,8 +158,9 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(const bf16* __r
   s_acc[warp][2 * lane + 1] = a1;
   __syncthreads();
   if (tid < 32) {
-    const float r0 = (s_acc[0][2 * tid] + s_acc[1][2 * tid]) + (s_acc[2][2 * tid] + s_acc[3][2 * tid]);
-    const float r1 = (s_acc[0][2 * tid + 1] + s_acc[1][2 * tid + 1]) + (s_acc[2][2 * tid + 1] + s_acc[3][2 * tid + 1]);
+    float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < AD_THREADS / 32; ++w) { r0 += s_acc[w][2 * tid]; r1 += s_acc[w][2 * tid + 1]; }
     *reinterpret_cast<uint32_t*>(o + (int64_t)b * ldo + h * 64 + 2 * tid) = pack_bf16x2(r0 * inv, r1 * inv);
   }
 }
