@@ -376,6 +376,40 @@ def measure_config5(batch=64, iters=3):
             "tflops": tf / ms * 1e3, "frac_of_peak": tf / ms * 1e3 / peak}
 
 
+def measure_decode(batch=32, n_new=124, reps=3):
+    """KV-cached greedy `generate()` -- the eval loop's call on the student and the pseudo-labelling loop's call
+    on the large-v3-shaped teacher (ref:training/run_distillation.py:1526, run_pseudo_labelling.py:903) -- tokens/s at `batch` clips,
+    128 tokens per row (4 initial + 124 generated, EOS never emitted), encoder included; best of `reps` calls after one that builds the
+    decode session and its CUDA graph."""
+    import time
+    from distil_whisper_b200.modeling import DistilWhisperB200ForConditionalGeneration
+    out = {"workload": f"greedy generate, {batch} x (80 x 3000 mel) -> 128 tokens per row, one CUDA-graph replay per token", "batch": batch}
+    for name, dims, dtype in (("teacher_large_v3_bf16", TEACHER, torch.bfloat16), ("student_distil_large_v3_fp32", STUDENT, None)):
+        torch.manual_seed(0)
+        with torch.device("cuda"):
+            m = DistilWhisperB200ForConditionalGeneration(dims)
+        if dtype is not None:
+            m = m.to(dtype)
+        feats = synthetic_batch(batch, 8, 3, dims, device="cuda")["input_features"]
+        kw = dict(max_new_tokens=n_new, eos_token_id=10 ** 6,
+                  decoder_input_ids=torch.tensor([[50258, 50259, 50360, 50364]], device="cuda").expand(batch, -1))
+        m.generate(feats, **kw)
+        best = 1e9
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ids = m.generate(feats, **kw)
+            torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        steps = ids.shape[1] - 1
+        out[name] = {"s_per_call": best, "tokens_per_s": batch * steps / best, "utterances_per_s": batch / best, "ms_per_token_step_incl_encoder": best / steps * 1e3}
+        del m, feats
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -466,6 +500,7 @@ def main():
         guarded("variants", other_variant)
         guarded("logmel", measure_logmel)
         guarded("config5", measure_config5)
+        guarded("decode", measure_decode)
         guarded("gpu_reference", lambda: time_hf_gpu(args.variant, 20, 5))
         if isinstance(out.get("gpu_reference"), dict) and out["gpu_reference"].get("value"):
             out["gpu_reference"]["speedup_of_this_repo"] = (utt / sec_e2e) / out["gpu_reference"]["value"]
